@@ -1,0 +1,198 @@
+/* mrt.h — C ABI of the B200-native path-tracing hot path of micro-raytracer.
+ *
+ * This header is the drop-in boundary.  It replaces the reference's `Sampler`
+ * struct API (the narrowest seam the per-pixel path-tracing loop sits behind):
+ *
+ *   Sampler::new(workers, n_dim)            /root/reference/src/sampler.rs:19
+ *   Sampler::execute(&scene, &frame, &rt)   /root/reference/src/sampler.rs:28
+ *   Sampler::img(&frame)                    /root/reference/src/sampler.rs:80
+ *
+ * called from CLI::raytrace (src/cli.rs:155-177) and HttpServer::raytrace
+ * (src/http.rs:136-148).  The descriptive structs below carry exactly the
+ * fields of the reference's Render/Scene/Frame types (src/rt.rs:10-190), as
+ * plain pointers and sizes.  All pointers are caller-owned HOST memory that is
+ * copied during the call.  Every entry point returns 0 on success and a
+ * non-zero mrt_status on error (message via mrt_last_error), never aborts —
+ * this is the C form of the reference's `Result<_, String>` convention
+ * (src/parser.rs:12-14).  One context = one caller thread; distinct contexts
+ * are independent (the reference makes one Sampler per HTTP connection thread,
+ * src/http.rs:138,155).
+ *
+ * There is NO CPU fallback behind this ABI: every entry point that computes
+ * runs hand-written sm_100a CUDA kernels and fails with MRT_ERR_CUDA when no
+ * device is usable.
+ */
+#ifndef MRT_H
+#define MRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRT_ABI_VERSION 1
+
+typedef enum mrt_status {
+    MRT_OK = 0,
+    MRT_ERR_INVALID = 1,   /* bad argument / scene the reference would panic on */
+    MRT_ERR_CUDA = 2,      /* CUDA runtime error, or no usable device            */
+    MRT_ERR_STATE = 3,     /* call order (e.g. execute before set_scene)         */
+    MRT_ERR_NOMEM = 4
+} mrt_status;
+
+/* RendererKind, src/rt.rs:137-144 */
+typedef enum mrt_kind {
+    MRT_SPHERE = 0,   /* param[0] = r                          rt.rs:120 */
+    MRT_PLANE = 1,    /* param[0..3] = n (not normalised)      rt.rs:123 */
+    MRT_BOX = 2,      /* param[0..3] = sizes (full extents)    rt.rs:126 */
+    MRT_TRIANGLE = 3, /* param[0..9] = v0,v1,v2                rt.rs:129 */
+    MRT_MESH = 4      /* mesh = index into mrt_scene.meshes    rt.rs:132 */
+} mrt_kind;
+
+/* Material, src/rt.rs:88-103.  Texture handles index mrt_scene.textures, -1 = None. */
+typedef struct mrt_material {
+    float albedo[3];
+    float rough, metal, glass, opacity, emit;
+    int32_t tex, rmap, mmap, gmap, omap, emap;
+} mrt_material;
+
+/* Renderer, src/rt.rs:152-158 (the never-read `aabb` field is dropped). */
+typedef struct mrt_object {
+    uint32_t kind;        /* mrt_kind */
+    uint32_t mesh;        /* MRT_MESH only */
+    float param[9];
+    uint32_t first_inst;  /* instances [first_inst, first_inst + n_inst) */
+    uint32_t n_inst;
+    mrt_material mat;
+} mrt_object;
+
+/* RendererInstance, src/rt.rs:146-150.  dir is (w, x, y, z) as serialised by
+ * src/lin.rs:428-443: xyz = facing vector, w = sin(roll). */
+typedef struct mrt_instance {
+    float pos[3];
+    float dir[4];
+} mrt_instance;
+
+/* Texture, src/rt.rs:81-86: row-major RGB f32 texels at texels[3*first_texel ...]. */
+typedef struct mrt_texture {
+    uint32_t w, h;
+    uint64_t first_texel;
+    uint32_t has_dat;     /* 0 ⇒ dat == None ⇒ every fetch returns zero (rt.rs:626) */
+    uint32_t _pad;
+} mrt_texture;
+
+/* Mesh, src/rt.rs:131-135: triangles [first_tri, first_tri + n_tri), 9 floats each.
+ * The depth-3 octree (src/parser.rs:805-824, src/rt.rs:630-703) is rebuilt by the library. */
+typedef struct mrt_mesh {
+    uint32_t first_tri;
+    uint32_t n_tri;
+} mrt_mesh;
+
+/* Light, src/rt.rs:160-175 */
+typedef enum mrt_light_kind { MRT_LIGHT_POINT = 0, MRT_LIGHT_DIR = 1 } mrt_light_kind;
+typedef struct mrt_light {
+    uint32_t kind;
+    float v[3];          /* Point: pos, Dir: dir */
+    float pwr;
+    float color[3];
+} mrt_light;
+
+/* Scene, src/rt.rs:183-190 (renderer_bvh is always None, src/parser.rs:922). */
+typedef struct mrt_scene {
+    const mrt_object* objects;     uint32_t n_objects;
+    const mrt_instance* instances; uint32_t n_instances;
+    const mrt_texture* textures;   uint32_t n_textures;
+    const float* texels;           uint64_t n_texels;     /* RGB triples */
+    const mrt_mesh* meshes;        uint32_t n_meshes;
+    const float* triangles;        uint32_t n_triangles;  /* 9 floats each */
+    const mrt_light* lights;       uint32_t n_lights;
+    float sky_color[3];
+    float sky_pwr;
+} mrt_scene;
+
+/* Frame + Camera, src/rt.rs:63-79 */
+typedef struct mrt_frame {
+    uint16_t res[2];
+    float ssaa;
+    float cam_pos[3];
+    float cam_dir[4];     /* (w, x, y, z) */
+    float fov, gamma, exp, aprt, foc;
+} mrt_frame;
+
+/* Deterministic per-ray probe record (closest_hit of the primary ray, rt.rs:867-898). */
+typedef struct mrt_hit {
+    float t0, t1;         /* entry / exit parameter; NaN-free; t0 = -1 on miss */
+    int32_t obj, inst;    /* object index, instance index within the object; -1 on miss */
+    int32_t tri0, tri1;   /* mesh triangle index of entry / exit hit, -1 if none */
+    float n0[3];          /* unit normal at the entry hit (rt.rs:776-793) */
+    float n1[3];          /* unit normal at the exit hit */
+    float uv[2];          /* to_uv of the entry hit point (rt.rs:795-809); 0 for meshes */
+    float orig[3];        /* primary ray origin and direction (rt.rs:900-931) */
+    float dir[3];
+} mrt_hit;
+
+typedef struct mrt_ctx mrt_ctx;
+
+/* ≙ Sampler::new(workers, n_dim), sampler.rs:19.  `workers`/`n_dim` (--worker/--dim) are
+ * accepted for signature parity and ignored: the CUDA grid replaces the tile pool. */
+int mrt_create(mrt_ctx** out, int device, uint32_t workers, uint32_t n_dim);
+void mrt_destroy(mrt_ctx* ctx);
+const char* mrt_last_error(const mrt_ctx* ctx);   /* ctx may be NULL: last create error */
+int mrt_abi_version(void);
+
+/* The three borrows of Sampler::execute (sampler.rs:28).  Data is validated, packed
+ * into the device layout and uploaded.  Changing scene or frame drops the accumulated
+ * passes (the reference would have to build a new Sampler). */
+int mrt_set_scene(mrt_ctx* ctx, const mrt_scene* scene);
+int mrt_set_frame(mrt_ctx* ctx, const mrt_frame* frame);
+/* RayTracer{bounce, loss} (rt.rs:16-22).  `seed` keys the counter-based RNG that stands
+ * in for rand::thread_rng (unseedable in the reference). */
+int mrt_set_rt(mrt_ctx* ctx, uint32_t bounce, float loss, uint64_t seed);
+
+/* Multi-GPU sample split: this context renders global sample indices
+ * rank, rank + world, rank + 2*world, ...  Default rank 0 of world 1. */
+int mrt_set_partition(mrt_ctx* ctx, uint32_t rank, uint32_t world);
+
+/* ≙ n_passes × Sampler::execute (sampler.rs:28-78): adds n_passes paths per supersampled
+ * pixel to the accumulation buffer.  Blocks until the device is done; *seconds (optional)
+ * receives the device time of the launches (CUDA events). */
+int mrt_execute(mrt_ctx* ctx, uint32_t n_passes, double* seconds);
+/* Same, without waiting: the launches are queued on the context's stream. */
+int mrt_execute_async(mrt_ctx* ctx, uint32_t n_passes);
+int mrt_sync(mrt_ctx* ctx);
+
+/* Drop the accumulated passes (≙ a fresh Sampler). */
+int mrt_reset(mrt_ctx* ctx);
+
+/* Geometry of the supersampled film: nw = (res.0 * ssaa) as usize (sampler.rs:29-30). */
+int mrt_film_size(mrt_ctx* ctx, uint32_t* nw, uint32_t* nh, uint32_t* passes);
+
+/* Linear accumulated sums, RGB f32, nw*nh*3 (what Sampler.colors holds, sampler.rs:14). */
+int mrt_accum(mrt_ctx* ctx, float* rgb, uint32_t* passes);
+/* Device view of the accumulator: nw*nh float4 (rgb + unused w), for an NCCL reduce by the
+ * host (one process per GPU).  mrt_set_passes records the pass count the summed buffer holds. */
+int mrt_accum_device(mrt_ctx* ctx, void** dptr, size_t* n_floats, void** cuda_stream);
+int mrt_set_passes(mrt_ctx* ctx, uint32_t passes);
+
+/* ≙ Sampler::img (sampler.rs:80-99): ÷passes, powf(gamma), extended-Reinhard, `as u8`,
+ * Lanczos3 resize nw×nh → res.  rgb = res.0*res.1*3 bytes. */
+int mrt_img(mrt_ctx* ctx, uint8_t* rgb);
+/* The u8 supersampled image before the resize (sampler.rs:84-96), nw*nh*3 bytes. */
+int mrt_img_ss(mrt_ctx* ctx, uint8_t* rgb);
+
+/* Deterministic probe: closest_hit of every primary ray with the lens jitter replaced by
+ * the lens centre (u = 0.5).  out = nw*nh records, row-major. */
+int mrt_trace_primary(mrt_ctx* ctx, mrt_hit* out);
+
+/* Counters of the kernels this context launched (bench.py's gpu_launches). */
+int mrt_launch_count(mrt_ctx* ctx, uint64_t* n);
+/* Measured FP32 FMA peak of the device this context lives on, in TFLOP/s
+ * (dependent-free FFMA microbenchmark, CUDA events); used as a live roofline denominator. */
+int mrt_fp32_peak(mrt_ctx* ctx, double* tflops, double* seconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRT_H */

@@ -1,0 +1,239 @@
+"""Host-side mirror of the reference's `Sampler` (src/sampler.rs:11-99) over the C ABI.
+
+    sampler = Sampler(workers, n_dim)              # ≙ Sampler::new      sampler.rs:19
+    dt = sampler.execute(scene, frame, rt)         # ≙ Sampler::execute  sampler.rs:28 (one pass)
+    img = sampler.img(frame)                       # ≙ Sampler::img      sampler.rs:80
+
+exactly as CLI::raytrace drives it (src/cli.rs:155-177).  All computation happens in the
+CUDA library `libmrt.so` (csrc/, built by __graft_entry__.build()); there is no CPU
+fallback — a missing library or device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import abi
+from .scene import Frame, PackedScene, RayTracer, Scene, pack_scene
+
+_LIB_NAME = "libmrt.so"
+_lib = None
+
+
+class MrtError(RuntimeError):
+    """≙ the String of the reference's Result<_, String>."""
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+
+def declare(lib, prefix: str = "mrt_"):
+    """Attach argtypes/restype for the entry points of include/mrt.h."""
+    P, u32, f32, u64 = C.c_void_p, C.c_uint32, C.c_float, C.c_uint64
+
+    def fn(name, *args, res=C.c_int):
+        f = getattr(lib, prefix + name)
+        f.argtypes, f.restype = list(args), res
+        return f
+
+    fn("create", C.POINTER(P), C.c_int, u32, u32) if prefix == "mrt_" else fn("create", C.POINTER(P), u32, u32)
+    fn("destroy", P, res=None)
+    fn("last_error", P, res=C.c_char_p)
+    fn("set_scene", P, C.POINTER(abi.MrtScene))
+    fn("set_frame", P, C.POINTER(abi.MrtFrame))
+    fn("set_rt", P, u32, f32, u64)
+    fn("set_partition", P, u32, u32)
+    fn("execute", P, u32, C.POINTER(C.c_double))
+    fn("reset", P)
+    fn("film_size", P, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32))
+    fn("accum", P, C.POINTER(f32), C.POINTER(u32))
+    fn("img", P, C.POINTER(C.c_uint8))
+    fn("img_ss", P, C.POINTER(C.c_uint8))
+    fn("trace_primary", P, C.c_void_p)
+    if prefix == "mrt_":
+        fn("abi_version")
+        fn("execute_async", P, u32)
+        fn("sync", P)
+        fn("accum_device", P, C.POINTER(P), C.POINTER(C.c_size_t), C.POINTER(P))
+        fn("set_passes", P, u32)
+        fn("launch_count", P, C.POINTER(u64))
+        fn("fp32_peak", P, C.POINTER(C.c_double), C.POINTER(C.c_double))
+    return lib
+
+
+def load_library():
+    """Load libmrt.so (in-tree).  Fails loudly: there is no other implementation."""
+    global _lib
+    if _lib is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise MrtError(f"{p} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+        _lib = declare(C.CDLL(p))
+        if _lib.mrt_abi_version() != 1:
+            raise MrtError("libmrt.so ABI version mismatch")
+    return _lib
+
+
+class _DeviceArray:
+    """Minimal __cuda_array_interface__ holder so torch can wrap the accumulator in place."""
+
+    def __init__(self, ptr: int, n: int, owner):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        self._owner = owner
+
+
+class Sampler:
+    """≙ `Sampler` of src/sampler.rs.  `workers` / `n_dim` (--worker / --dim, cli.rs:157) are
+    accepted and ignored: the CUDA grid replaces the tile pool."""
+
+    prefix = "mrt_"
+
+    def __init__(self, workers: int = 24, n_dim: int = 64, device: int = 0, seed: int = 0x5EED, _lib=None):
+        self._lib = _lib if _lib is not None else load_library()
+        self._ctx = C.c_void_p()
+        self._create(workers, n_dim, device)
+        self.seed = seed
+        self._scene_key = None
+        self._frame_key = None
+        self._rt_key = None
+        self._packed: Optional[PackedScene] = None
+
+    # -- plumbing
+    def _f(self, name):
+        return getattr(self._lib, self.prefix + name)
+
+    def _create(self, workers, n_dim, device):
+        rc = self._lib.mrt_create(C.byref(self._ctx), int(device), int(workers), int(n_dim))
+        if rc:
+            raise MrtError((self._lib.mrt_last_error(None) or b"mrt_create failed").decode())
+
+    def _check(self, rc):
+        if rc:
+            raise MrtError((self._f("last_error")(self._ctx) or b"error").decode())
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._f("destroy")(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # -- uploads (the three borrows of Sampler::execute); re-sent only when they change
+    def set_scene(self, scene):
+        packed = scene if isinstance(scene, PackedScene) else pack_scene(scene)
+        self._check(self._f("set_scene")(self._ctx, C.byref(packed.c)))
+        self._packed = packed
+
+    def set_frame(self, frame: Frame):
+        f = frame.pack()
+        self._check(self._f("set_frame")(self._ctx, C.byref(f)))
+
+    def set_rt(self, rt: RayTracer):
+        self._check(self._f("set_rt")(self._ctx, int(rt.bounce), float(rt.loss), int(self.seed)))
+
+    def set_partition(self, rank: int, world: int):
+        self._check(self._f("set_partition")(self._ctx, int(rank), int(world)))
+
+    def _bind(self, scene, frame: Frame, rt: RayTracer):
+        sk = id(scene)
+        if sk != self._scene_key:
+            self.set_scene(scene)
+            self._scene_key = sk
+            self._scene_ref = scene
+        fk = (tuple(frame.res), frame.ssaa, tuple(frame.cam.pos), tuple(frame.cam.dir), frame.cam.fov,
+              frame.cam.gamma, frame.cam.exp, frame.cam.aprt, frame.cam.foc)
+        if fk != self._frame_key:
+            self.set_frame(frame)
+            self._frame_key = fk
+        rk = (rt.bounce, rt.loss, self.seed)
+        if rk != self._rt_key:
+            self.set_rt(rt)
+            self._rt_key = rk
+
+    # -- the reference API
+    def execute(self, scene, frame: Frame, rt: RayTracer, n_passes: int = 1) -> float:
+        """One pass (or n_passes) = one path per supersampled pixel; returns seconds."""
+        self._bind(scene, frame, rt)
+        sec = C.c_double()
+        self._check(self._f("execute")(self._ctx, int(n_passes), C.byref(sec)))
+        return sec.value
+
+    def img(self, frame: Optional[Frame] = None) -> np.ndarray:
+        """(res_h, res_w, 3) uint8, ≙ Sampler::img."""
+        if frame is not None and self._frame_key is None:
+            self.set_frame(frame)
+        w, h = self._res
+        out = np.empty((h, w, 3), np.uint8)
+        self._check(self._f("img")(self._ctx, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    # -- extras used by tests / bench
+    @property
+    def _res(self) -> Tuple[int, int]:
+        fk = self._frame_key
+        if fk is None:
+            raise MrtError("no frame set")
+        return fk[0]
+
+    def film_size(self) -> Tuple[int, int, int]:
+        nw, nh, p = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._check(self._f("film_size")(self._ctx, C.byref(nw), C.byref(nh), C.byref(p)))
+        return nw.value, nh.value, p.value
+
+    def reset(self):
+        self._check(self._f("reset")(self._ctx))
+
+    def accum(self) -> Tuple[np.ndarray, int]:
+        nw, nh, _ = self.film_size()
+        out = np.empty((nh, nw, 3), np.float32)
+        p = C.c_uint32()
+        self._check(self._f("accum")(self._ctx, out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(p)))
+        return out, p.value
+
+    def img_ss(self) -> np.ndarray:
+        nw, nh, _ = self.film_size()
+        out = np.empty((nh, nw, 3), np.uint8)
+        self._check(self._f("img_ss")(self._ctx, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def trace_primary(self) -> np.ndarray:
+        nw, nh, _ = self.film_size()
+        out = np.zeros((nh, nw), dtype=np.dtype(abi.HIT_DTYPE))
+        assert out.dtype.itemsize == C.sizeof(abi.MrtHit)
+        self._check(self._f("trace_primary")(self._ctx, out.ctypes.data))
+        return out
+
+    # -- CUDA-only
+    def execute_async(self, n_passes: int):
+        self._check(self._lib.mrt_execute_async(self._ctx, int(n_passes)))
+
+    def sync(self):
+        self._check(self._lib.mrt_sync(self._ctx))
+
+    def accum_device(self):
+        """(object exposing __cuda_array_interface__ over nw*nh*4 floats, stream handle)."""
+        p, n, s = C.c_void_p(), C.c_size_t(), C.c_void_p()
+        self._check(self._lib.mrt_accum_device(self._ctx, C.byref(p), C.byref(n), C.byref(s)))
+        return _DeviceArray(p.value, n.value, self), s.value
+
+    def set_passes(self, passes: int):
+        self._check(self._lib.mrt_set_passes(self._ctx, int(passes)))
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        self._check(self._lib.mrt_launch_count(self._ctx, C.byref(n)))
+        return n.value
+
+    def fp32_peak(self) -> Tuple[float, float]:
+        t, s = C.c_double(), C.c_double()
+        self._check(self._lib.mrt_fp32_peak(self._ctx, C.byref(t), C.byref(s)))
+        return t.value, s.value
