@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the path-tracing hot path (contract: see the task brief).
+
+Workload (BASELINE.json `metric`, configs[1]): CornellBox2 — 7 boxes + sphere + emissive
+panel — 1080x1080, ssaa 2 (2160x2160 film), 1024 spp, bounce 8: 4 777 574 400 paths.
+One "step" = one full render of that image.  At N GPUs the 1024 samples are split over the
+ranks (rank r renders global samples r, r+N, ...; strong scaling) and the accumulation
+buffers are summed onto rank 0 by one NCCL reduce over NVLink.
+
+  value   Mpaths/s, scene resident on the device, render + reduce only (CUDA events, max over ranks)
+  e2e     Mpaths/s through the reference-facing call sequence with HOST buffers inside the timed
+          region: set_scene (H2D) -> execute(1024 passes) -> reduce -> img() (tonemap + Lanczos3
+          + D2H of the u8 image)
+  roofline  FP32: achieved = algorithmic flops per path-kernel launch / measured launch duration
+  cpu_baseline  the CPU oracle (a literal port of the reference; the Rust binary cannot be built
+          here) on the box's host cores, bounded sample of the same workload
+
+`--impl reference` times that CPU port on all host threads (rank 0 only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SCENE = os.path.join(ROOT, "tests", "golden", "scenes", "CornellBox2.json")
+# flops/path = 60 + S*sum_inst(36 + C_kind) + H*153, CornellBox2: sum_inst = 533,
+# S = 6.709 closest-hit calls and H = 6.178 hits per path (measured by the oracle, tests/test_oracle_stats.py)
+FLOPS_PER_PATH = 60.0 + 6.709 * 533.0 + 6.178 * 153.0
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.45: SMs x lanes x FMA x max SM clock
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        rows = [r for t, r in self.rows if len(r) >= 9 and (t0 is None or t0 - 0.05 <= t <= t1 + 0.05)] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def load_scene(args):
+    import micro_raytracer_b200 as mrt
+    r = mrt.load_render(SCENE)
+    r.rt.sample = args.spp
+    if args.res:
+        r.frame.res = (args.res, args.res)
+    return r
+
+
+def run_reference(args, rank):
+    """The reference's CPU implementation of the path: the oracle port, all host threads."""
+    if rank != 0:
+        return
+    import oracle_lib
+    r = load_scene(args)
+    cpu = oracle_lib.OracleSampler(workers=0, mode=oracle_lib.FORWARD)
+    nw, nh = r.frame.film_size()
+    cores = os.cpu_count() or 1
+    passes = max(1, args.ref_passes)
+    cpu._bind(r.scene, r.frame, r.rt)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu.execute(r.scene, r.frame, r.rt, 1)
+    times = []
+    for _ in range(args.steps):
+        cpu.reset()
+        t0 = time.perf_counter()
+        cpu.execute(r.scene, r.frame, r.rt, passes)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    val = nw * nh * passes * args.steps / total / 1e6
+    sample = f"{passes} of {args.spp} passes of the full {nw}x{nh} film per step (per-pass cost is constant)"
+    line = {
+        "impl": "reference", "metric": "Mpaths/s", "value": val, "unit": "Mpaths/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, nw, nh),
+        "cpu_baseline": {"value": val, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "literal C++ port of rt.rs/sampler.rs, single trace per path; the Rust reference traces each path twice (rt.rs:957,961)"},
+        "e2e": {"value": val, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, nw, nh):
+    return {"workload": f"CornellBox2.json {args.res or 1080}x{args.res or 1080} ssaa2 ({nw}x{nh} film) {args.spp} spp bounce 8 loss 0.15",
+            "paths_per_step": nw * nh * args.spp, "parallelism": f"sample-split x{args.gpus} + NCCL reduce" if args.gpus > 1 else "single GPU",
+            "l2": "no input reuse across steps: per step the only global traffic is the 74.6 MB accumulator (> L2 share), scene lives in the constant bank",
+            "spp_per_launch": int(os.environ.get("MRT_SPP_PER_LAUNCH", "128"))}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--spp", type=int, default=1024)
+    ap.add_argument("--res", type=int, default=0, help="debug: square output resolution instead of 1080")
+    ap.add_argument("--ref-passes", type=int, default=4, help="passes per step of the CPU reference arm")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import micro_raytracer_b200 as mrt
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE {world}"
+    n_gpus = world
+
+    r = load_scene(args)
+    nw, nh = r.frame.film_size()
+    spp = args.spp
+    my_passes = len(range(rank, spp, world))
+    packed = mrt.pack_scene(r.scene)
+
+    s = mrt.Sampler(device=local_rank)
+    # a real (non-legacy) stream shared by torch (events, NCCL ordering) and the C-ABI context
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    s.set_stream(stream.cuda_stream)
+    s._bind(packed, r.frame, r.rt)
+    s.set_partition(rank, world)
+    acc_dev, _ = s.accum_device()
+    acc = torch.as_tensor(acc_dev, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def render_step():
+        s.reset()
+        s.execute_async(my_passes)
+        if world > 1:
+            dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
+        s.set_passes(spp)
+
+    out_img = np.empty((r.frame.res[1], r.frame.res[0], 3), np.uint8)
+
+    def e2e_step():
+        s.set_scene(packed)           # H2D: scene description from host buffers
+        s.set_partition(rank, world)
+        s.execute_async(my_passes)
+        if world > 1:
+            dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
+        s.set_passes(spp)
+        if rank == 0:
+            out_img[...] = s.img(r.frame)   # tonemap + Lanczos3 + D2H of the u8 image
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        render_step()
+    barrier()
+
+    # ---- per-launch duration of the dominant kernel (rank-local, CUDA events on the launch stream)
+    s.reset()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    spl = int(os.environ.get("MRT_SPP_PER_LAUNCH", "128"))
+    n_launch = -(-my_passes // spl)
+    ev[0].record(stream)
+    s.execute_async(my_passes)
+    ev[1].record(stream)
+    torch.cuda.synchronize(dev)
+    launch_ms = ev[0].elapsed_time(ev[1]) / n_launch
+    paths_per_launch = nw * nh * my_passes / n_launch
+
+    # ---- timed region: K render steps, device timed, clocks sampled
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    l0 = s.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        render_step()
+    e1.record(stream)
+    barrier()
+    tw1 = time.perf_counter()
+    launches = s.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    lt = torch.tensor([float(launches)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    clk = clocks.stop(tw0, tw1) if rank == 0 else None
+    total_ms = float(ms.item())
+    paths_per_step = nw * nh * spp
+    value = paths_per_step * args.steps / (total_ms * 1e-3) / 1e6
+
+    # ---- e2e: host buffers in, u8 image out, wall clock between syncs
+    for _ in range(1):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    t1 = time.perf_counter()
+    e2e_t = torch.tensor([t1 - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = paths_per_step * args.steps / float(e2e_t.item()) / 1e6
+
+    if rank == 0:
+        peak_tf, _ = s.fp32_peak()
+        ach_tf = paths_per_launch * FLOPS_PER_PATH / (launch_ms * 1e-3) / 1e12
+        line = {
+            "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, nw, nh),
+            "clocks": clk,
+            "e2e": {"value": e2e_val, "unit": "Mpaths/s", "h2d_bytes_per_step": packed.nbytes(),
+                    "d2h_bytes_per_step": int(out_img.nbytes), "ms_per_step": 1e3 * float(e2e_t.item()) / args.steps},
+            "gpu_launches": int(lt.item()),
+            "roofline": {"bound": "fp32", "kernel": "path_kernel_param<0>", "achieved": ach_tf, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
+                         "peak_source": "FFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
+                         "peak_nominal": FP32_NOMINAL_TFLOPS, "frac_of_nominal": ach_tf / FP32_NOMINAL_TFLOPS,
+                         "flops_per_path": FLOPS_PER_PATH, "paths_per_launch": paths_per_launch, "launch_ms": launch_ms,
+                         "roofline_mpaths_per_gpu": FP32_NOMINAL_TFLOPS * 1e12 / FLOPS_PER_PATH / 1e6},
+            "image_mean_u8": float(out_img.mean()),
+        }
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            try:
+                line["roofline"]["traffic"] = json.load(open(prof)).get("path_kernel_bytes_per_launch")
+            except Exception:  # noqa: BLE001
+                pass
+        if not args.no_cpu_baseline and n_gpus == 1:
+            line["cpu_baseline"] = cpu_baseline(args, r, nw, nh)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, r, nw, nh):
+    """The oracle (port of the reference) on the host cores, bounded sample: whole passes of the
+    full film until ~cpu_baseline_seconds have elapsed."""
+    import oracle_lib
+    cpu = oracle_lib.OracleSampler(workers=0, mode=oracle_lib.FORWARD)
+    cpu._bind(r.scene, r.frame, r.rt)
+    n, t = 0, 0.0
+    while t < args.cpu_baseline_seconds and n < args.spp:
+        t += cpu.execute(r.scene, r.frame, r.rt, 1)
+        n += 1
+    return {"value": nw * nh * n / t / 1e6, "unit": "Mpaths/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{n} of {args.spp} passes of the full {nw}x{nh} film ({t:.1f} s)",
+            "note": "literal C++ port, single trace per path; the Rust reference traces every path twice (rt.rs:957,961)"}
+
+
+if __name__ == "__main__":
+    main()

@@ -175,6 +175,10 @@ int mrt_accum(mrt_ctx* ctx, float* rgb, uint32_t* passes);
  * host (one process per GPU).  mrt_set_passes records the pass count the summed buffer holds. */
 int mrt_accum_device(mrt_ctx* ctx, void** dptr, size_t* n_floats, void** cuda_stream);
 int mrt_set_passes(mrt_ctx* ctx, uint32_t passes);
+/* Run this context's work on a caller-owned CUDA stream (a cudaStream_t / CUstream handle, e.g.
+ * torch.cuda.current_stream().cuda_stream) so that the host can order it with its own events
+ * and collectives.  NULL restores the context's private stream. */
+int mrt_set_stream(mrt_ctx* ctx, void* cuda_stream);
 
 /* ≙ Sampler::img (sampler.rs:80-99): ÷passes, powf(gamma), extended-Reinhard, `as u8`,
  * Lanczos3 resize nw×nh → res.  rgb = res.0*res.1*3 bytes. */

@@ -88,6 +88,6 @@ MRT_SYMBOLS = [
     "mrt_create", "mrt_destroy", "mrt_last_error", "mrt_abi_version",
     "mrt_set_scene", "mrt_set_frame", "mrt_set_rt", "mrt_set_partition",
     "mrt_execute", "mrt_execute_async", "mrt_sync", "mrt_reset", "mrt_film_size",
-    "mrt_accum", "mrt_accum_device", "mrt_set_passes", "mrt_img", "mrt_img_ss",
+    "mrt_accum", "mrt_accum_device", "mrt_set_passes", "mrt_set_stream", "mrt_img", "mrt_img_ss",
     "mrt_trace_primary", "mrt_launch_count", "mrt_fp32_peak",
 ]

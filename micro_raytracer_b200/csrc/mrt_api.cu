@@ -1,0 +1,690 @@
+// mrt_api.cu — the C ABI of include/mrt.h: context, scene packing into the device layout
+// (SlimInst/FatInst/Xf/lights/textures/flattened mesh octree), launch scheduling, film
+// read-out.  Host code only; every pixel is computed by the kernels in mrt_kernels.cu.
+// There is no CPU fallback: without a usable CUDA device every compute entry point fails.
+#include "mrt_device.cuh"
+#include "mrt_kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_create_err;
+
+// ---------------------------------------------------------------- host f32 math (lin.rs order)
+struct H3 { float x, y, z; };
+inline H3 hsub(H3 a, H3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline H3 hcross(H3 a, H3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline float hdot(H3 a, H3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline H3 hnorm(H3 a) { float r = 1.0f / std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); return {a.x * r, a.y * r, a.z * r}; }
+struct HM { float m[9]; };
+inline H3 hmul(const HM& m, H3 v) {
+    return {m.m[0] * v.x + m.m[1] * v.y + m.m[2] * v.z, m.m[3] * v.x + m.m[4] * v.y + m.m[5] * v.z,
+            m.m[6] * v.x + m.m[7] * v.y + m.m[8] * v.z};
+}
+// M = rotate_y(dir) * lookat(dir, up): lin.rs:175-183, 197-209; applied as rot_y * (look * v)
+HM transform_of(const float dir[4]) {
+    const float w = dir[0];
+    const float cw = std::sqrt(1.0f - w * w);
+    const HM ry = {{cw, 0.0f, w, 0.0f, 1.0f, 0.0f, -w, 0.0f, cw}};
+    const H3 fwd = hnorm({dir[1], dir[2], dir[3]});
+    const H3 right = hnorm(hcross(fwd, {0.0f, 0.0f, 1.0f}));
+    const H3 up = hcross(right, fwd);
+    const HM lk = {{right.x, -right.y, right.z, -fwd.x, fwd.y, -fwd.z, up.x, -up.y, up.z}};
+    HM out;
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++)
+            out.m[3 * r + c] = ry.m[3 * r] * lk.m[c] + ry.m[3 * r + 1] * lk.m[3 + c] + ry.m[3 * r + 2] * lk.m[6 + c];
+    return out;
+}
+bool is_identity(const HM& m) {
+    const float id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int i = 0; i < 9; i++)
+        if (!(m.m[i] == id[i])) return false;
+    return true;
+}
+bool finite_m(const HM& m) {
+    for (float v : m.m) if (!std::isfinite(v)) return false;
+    return true;
+}
+inline float u2f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t upload(const std::vector<T>& h) {
+        release();
+        n = h.size();
+        const size_t bytes = std::max<size_t>(1, n) * sizeof(T);
+        cudaError_t e = cudaMalloc((void**)&p, bytes);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        if (n) e = cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice);
+        return e;
+    }
+    cudaError_t alloc(size_t count) {
+        if (p && n == count) return cudaSuccess;
+        release();
+        n = count;
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(1, n) * sizeof(T));
+        if (e != cudaSuccess) p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct mrt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;      // the stream work is queued on
+    cudaStream_t own_stream = nullptr;  // created by mrt_create
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    // scene
+    bool have_scene = false, in_param = false;
+    uint32_t features = 0;
+    ParamScene* pscene = nullptr;  // host staging copies of the kernel-parameter structs
+    GlobalScene gscene{};
+    DevBuf<SlimInst> d_slim;
+    DevBuf<Xf> d_xf;
+    DevBuf<FatInst> d_fat;
+    DevBuf<DTex> d_tex;
+    DevBuf<float4> d_texels;
+    DevBuf<DMesh> d_mesh;
+    DevBuf<DMeshLeaf> d_leaf;
+    DevBuf<uint32_t> d_leaf_idx;
+    DevBuf<DTri> d_tri;
+    DevBuf<uint32_t> d_obj_inst;
+
+    // frame / rt
+    bool have_frame = false;
+    mrt_frame frame{};
+    uint32_t nw = 0, nh = 0;
+    uint32_t bounce = 8;
+    float loss = 0.15f;
+    uint64_t seed = 0x5EED;
+    uint32_t rank = 0, world = 1;
+    uint32_t passes = 0;        // passes this context rendered (local)
+    uint32_t passes_total = 0;  // passes the accumulator holds (after an external reduce)
+    uint32_t spp_per_launch = 128;
+
+    // film
+    DevBuf<float4> d_accum;
+    DevBuf<uint8_t> d_ss, d_out;
+    DevBuf<float> d_tmp, d_rgb, d_wv, d_wh;
+    DevBuf<int32_t> d_lv, d_cv, d_lh, d_ch;
+    DevBuf<mrt_hit> d_hits;
+    uint32_t taps_v = 0, taps_h = 0;
+    bool weights_ready = false;
+
+    ~mrt_ctx() { delete pscene; }
+};
+
+namespace {
+
+int fail(mrt_ctx* c, int code, const std::string& m) { c->err = m; return code; }
+int cuda_fail(mrt_ctx* c, cudaError_t e, const char* what) {
+    c->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return MRT_ERR_CUDA;
+}
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(c, e__, #call); } while (0)
+
+uint32_t fold_seed(uint64_t seed) { return (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u); }
+
+void film_dims(const mrt_frame& f, uint32_t* nw, uint32_t* nh) {  // sampler.rs:29-30
+    auto cast = [](float v) -> uint32_t { return v > 0.0f ? (v >= 4294967040.0f ? 0xffffffffu : (uint32_t)v) : 0u; };
+    *nw = cast((float)f.res[0] * f.ssaa);
+    *nh = cast((float)f.res[1] * f.ssaa);
+}
+
+FilmParams make_film_params(const mrt_ctx* c) {
+    FilmParams fp{};
+    const mrt_frame& f = c->frame;
+    fp.accum = c->d_accum.p;
+    fp.nw = c->nw; fp.nh = c->nh;
+    fp.key = fold_seed(c->seed);
+    fp.max_bounce = c->bounce;
+    fp.keep = 1.0f - std::fmin(c->loss, 1.0f);
+    fp.cam_pos[0] = f.cam_pos[0]; fp.cam_pos[1] = f.cam_pos[1]; fp.cam_pos[2] = f.cam_pos[2];
+    fp.aprt = f.aprt; fp.foc = f.foc;
+    const HM m = transform_of(f.cam_dir);
+    for (int i = 0; i < 9; i++) fp.cam_M[i] = m.m[i];
+    fp.fw = (float)f.res[0] * f.ssaa;
+    fp.fh = (float)f.res[1] * f.ssaa;
+    const float tan_fov = std::tan((0.5f * f.fov) * (3.14159265358979323846f / 180.0f));  // rt.rs:902
+    fp.fy = 1.0f / (2.0f * tan_fov);
+    return fp;
+}
+
+// Flattened depth-3 octree of one mesh: the non-empty leaves in the reference's depth-first
+// child order (rt.rs:631-689, parser.rs:805-824), each with the triangles that have a vertex
+// inside it (rt.rs:227-248).
+struct LeafBuild { H3 center, size; std::vector<uint32_t> idx; };
+void build_leaves(const float* tris, uint32_t n_tri, std::vector<LeafBuild>* out) {
+    static const float G[8][3] = {{1, 1, 1}, {-1, 1, 1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, -1}, {1, -1, -1}};
+    float mx = 0, my = 0, mz = 0;  // Mesh::gen_aabb, rt.rs:261-270
+    for (uint32_t t = 0; t < n_tri; t++)
+        for (int v = 0; v < 3; v++) {
+            const float* p = tris + 9 * (size_t)t + 3 * v;
+            mx = std::fmax(mx, std::fabs(p[0])); my = std::fmax(my, std::fabs(p[1])); mz = std::fmax(mz, std::fabs(p[2]));
+        }
+    const H3 A0 = {2.0f * mx, 2.0f * my, 2.0f * mz};
+    const H3 A1 = {0.5f * A0.x, 0.5f * A0.y, 0.5f * A0.z};
+    const H3 A2 = {0.5f * A1.x, 0.5f * A1.y, 0.5f * A1.z};
+    const H3 A3 = {0.5f * A2.x, 0.5f * A2.y, 0.5f * A2.z};
+    for (int i0 = 0; i0 < 8; i0++) {
+        const H3 r1 = {0.0f + A0.x * (G[i0][0] * 0.25f), 0.0f + A0.y * (G[i0][1] * 0.25f), 0.0f + A0.z * (G[i0][2] * 0.25f)};
+        for (int i1 = 0; i1 < 8; i1++) {
+            const H3 r2 = {r1.x + A1.x * (G[i1][0] * 0.25f), r1.y + A1.y * (G[i1][1] * 0.25f), r1.z + A1.z * (G[i1][2] * 0.25f)};
+            for (int i2 = 0; i2 < 8; i2++) {
+                const H3 r3 = {r2.x + A2.x * (G[i2][0] * 0.25f), r2.y + A2.y * (G[i2][1] * 0.25f), r2.z + A2.z * (G[i2][2] * 0.25f)};
+                const H3 hi = {r3.x + 0.5f * A3.x, r3.y + 0.5f * A3.y, r3.z + 0.5f * A3.z};
+                const H3 lo = {r3.x - 0.5f * A3.x, r3.y - 0.5f * A3.y, r3.z - 0.5f * A3.z};
+                LeafBuild lb{r3, A3, {}};
+                for (uint32_t t = 0; t < n_tri; t++) {
+                    bool in = false;
+                    for (int v = 0; v < 3 && !in; v++) {
+                        const float* p = tris + 9 * (size_t)t + 3 * v;
+                        in = !(p[0] > hi.x || p[1] > hi.y || p[2] > hi.z) && !(p[0] < lo.x || p[1] < lo.y || p[2] < lo.z);
+                    }
+                    if (in) lb.idx.push_back(t);
+                }
+                if (!lb.idx.empty()) out->push_back(std::move(lb));
+            }
+        }
+    }
+}
+
+uint32_t pack_ids(int32_t lo, int32_t hi) { return ((uint32_t)(lo < 0 ? 0xffff : lo) & 0xffffu) | (((uint32_t)(hi < 0 ? 0xffff : hi) & 0xffffu) << 16); }
+
+}  // namespace
+
+extern "C" {
+
+int mrt_abi_version(void) { return MRT_ABI_VERSION; }
+
+const char* mrt_last_error(const mrt_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int mrt_create(mrt_ctx** out, int device, uint32_t workers, uint32_t n_dim) {
+    (void)workers; (void)n_dim;  // --worker / --dim: the CUDA grid replaces the tile pool
+    if (!out) { g_create_err = "mrt_create: null out"; return MRT_ERR_INVALID; }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_err = std::string("mrt_create: no CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0") + "); there is no CPU fallback";
+        return MRT_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { g_create_err = "mrt_create: device index out of range"; return MRT_ERR_INVALID; }
+    mrt_ctx* c = new mrt_ctx();
+    c->device = device;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    c->stream = c->own_stream;
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e != cudaSuccess) {
+        g_create_err = std::string("mrt_create: ") + cudaGetErrorString(e);
+        delete c;
+        return MRT_ERR_CUDA;
+    }
+    if (const char* s = std::getenv("MRT_SPP_PER_LAUNCH")) {
+        const int v = std::atoi(s);
+        if (v > 0) c->spp_per_launch = (uint32_t)v;
+    }
+    c->pscene = new ParamScene();
+    *out = c;
+    return MRT_OK;
+}
+
+void mrt_destroy(mrt_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->d_slim.release(); c->d_xf.release(); c->d_fat.release(); c->d_tex.release(); c->d_texels.release();
+    c->d_mesh.release(); c->d_leaf.release(); c->d_leaf_idx.release(); c->d_tri.release(); c->d_obj_inst.release();
+    c->d_accum.release(); c->d_ss.release(); c->d_out.release(); c->d_tmp.release(); c->d_rgb.release();
+    c->d_wv.release(); c->d_wh.release(); c->d_lv.release(); c->d_cv.release(); c->d_lh.release(); c->d_ch.release();
+    c->d_hits.release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int mrt_reset(mrt_ctx* c) {
+    if (!c) return MRT_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    c->passes = 0;
+    c->passes_total = 0;
+    if (c->d_accum.p) CK(cudaMemsetAsync(c->d_accum.p, 0, c->d_accum.n * sizeof(float4), c->stream));
+    return MRT_OK;
+}
+
+int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
+    if (!c || !s) return MRT_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    if (s->n_lights > MRT_MAX_LIGHTS) return fail(c, MRT_ERR_INVALID, "more than 16 lights are not supported");
+    if (s->n_objects > 0xffffu) return fail(c, MRT_ERR_INVALID, "too many objects");
+    if (s->n_textures >= 0xffffu) return fail(c, MRT_ERR_INVALID, "too many textures");
+
+    uint32_t feat = s->n_lights ? F_LIGHTS : 0u;
+    // textures -> float4 texels
+    std::vector<DTex> tex(s->n_textures);
+    std::vector<float4> texels;
+    for (uint32_t i = 0; i < s->n_textures; i++) {
+        const mrt_texture& t = s->textures[i];
+        const uint64_t n = (uint64_t)t.w * t.h;
+        tex[i] = {t.w, t.h, (uint32_t)texels.size(), (t.has_dat && n > 0) ? 1u : 0u};
+        if (tex[i].has_dat) {
+            if (t.first_texel + n > s->n_texels) return fail(c, MRT_ERR_INVALID, "texture texel range out of bounds");
+            if (texels.size() + n > 0x7fffffffull) return fail(c, MRT_ERR_INVALID, "textures too large");
+            for (uint64_t k = 0; k < n; k++) {
+                const float* p = s->texels + 3 * (t.first_texel + k);
+                texels.push_back(make_float4(p[0], p[1], p[2], 0.0f));
+            }
+        }
+    }
+    // meshes -> leaves + triangles
+    std::vector<DMesh> meshes(s->n_meshes);
+    std::vector<DMeshLeaf> leaves;
+    std::vector<uint32_t> leaf_idx;
+    std::vector<DTri> tris;
+    for (uint32_t i = 0; i < s->n_meshes; i++) {
+        const mrt_mesh& m = s->meshes[i];
+        if ((uint64_t)m.first_tri + m.n_tri > s->n_triangles) return fail(c, MRT_ERR_INVALID, "mesh triangle range out of bounds");
+        if (m.n_tri == 0) return fail(c, MRT_ERR_INVALID, "empty mesh");
+        const float* tp = s->triangles + 9 * (size_t)m.first_tri;
+        std::vector<LeafBuild> lb;
+        build_leaves(tp, m.n_tri, &lb);
+        if (lb.empty()) return fail(c, MRT_ERR_INVALID, "mesh octree is empty (the reference would panic, rt.rs:717)");
+        meshes[i] = {(uint32_t)leaves.size(), (uint32_t)lb.size(), (uint32_t)tris.size(), m.n_tri};
+        for (const LeafBuild& l : lb) {
+            DMeshLeaf dl;
+            dl.lo = make_float4(l.center.x - 0.5f * l.size.x, l.center.y - 0.5f * l.size.y, l.center.z - 0.5f * l.size.z, u2f((uint32_t)leaf_idx.size()));
+            dl.hi = make_float4(l.center.x + 0.5f * l.size.x, l.center.y + 0.5f * l.size.y, l.center.z + 0.5f * l.size.z, u2f((uint32_t)l.idx.size()));
+            leaves.push_back(dl);
+            leaf_idx.insert(leaf_idx.end(), l.idx.begin(), l.idx.end());
+        }
+        for (uint32_t t = 0; t < m.n_tri; t++) {
+            const float* p = tp + 9 * (size_t)t;
+            DTri d;
+            d.v0 = make_float4(p[0], p[1], p[2], 0.0f);
+            d.e0 = make_float4(p[3] - p[0], p[4] - p[1], p[5] - p[2], 0.0f);
+            d.e1 = make_float4(p[6] - p[0], p[7] - p[1], p[8] - p[2], 0.0f);
+            tris.push_back(d);
+        }
+    }
+    // instances
+    std::vector<SlimInst> slim;
+    std::vector<FatInst> fat;
+    std::vector<Xf> xfs;
+    std::vector<uint32_t> obj_inst;
+    for (uint32_t oi = 0; oi < s->n_objects; oi++) {
+        const mrt_object& o = s->objects[oi];
+        const mrt_material& mt = o.mat;
+        if (o.kind > MRT_MESH) return fail(c, MRT_ERR_INVALID, "unknown object kind");
+        if (o.kind == MRT_TRIANGLE)
+            return fail(c, MRT_ERR_INVALID, "top-level triangle objects panic in the reference (Triangle::gen_aabb is todo!(), rt.rs:224); use a mesh");
+        if (o.kind == MRT_MESH && o.mesh >= s->n_meshes) return fail(c, MRT_ERR_INVALID, "mesh index out of range");
+        if ((uint64_t)o.first_inst + o.n_inst > s->n_instances) return fail(c, MRT_ERR_INVALID, "instance range out of bounds");
+        if (o.n_inst > 0xffffu) return fail(c, MRT_ERR_INVALID, "too many instances in one object");
+        if (!(mt.emit >= 0.0f && mt.emit <= 1.0f)) return fail(c, MRT_ERR_INVALID, "material emit outside [0,1] (gen_bool panics, rt.rs:968)");
+        if (!(mt.opacity >= 0.0f && mt.opacity <= 1.0f)) return fail(c, MRT_ERR_INVALID, "material opacity outside [0,1] (gen_bool panics, rt.rs:1054)");
+        const int32_t ids[6] = {mt.tex, mt.rmap, mt.mmap, mt.gmap, mt.omap, mt.emap};
+        bool textured = false;
+        for (int32_t id : ids) {
+            if (id >= (int32_t)s->n_textures) return fail(c, MRT_ERR_INVALID, "texture index out of range");
+            textured |= id >= 0;
+        }
+        if (textured && o.kind == MRT_MESH) return fail(c, MRT_ERR_INVALID, "textured mesh: to_uv is todo!() in the reference (rt.rs:806)");
+        if (textured) feat |= F_TEX;
+        if (mt.opacity < 1.0f || mt.omap >= 0) feat |= F_TRANSMIT;
+        if (o.kind == MRT_MESH) feat |= F_MESH;
+        for (uint32_t k = 0; k < o.n_inst; k++) {
+            const mrt_instance& in = s->instances[o.first_inst + k];
+            const float nd[4] = {-in.dir[0], -in.dir[1], -in.dir[2], -in.dir[3]};  // rt.rs:726: -inst.dir
+            const HM M = transform_of(nd);
+            if (!finite_m(M)) return fail(c, MRT_ERR_INVALID, "instance dir gives a non-finite transform (|w| > 1, zero or vertical facing vector)");
+            const bool ident = is_identity(M);
+            const H3 pos = {in.pos[0], in.pos[1], in.pos[2]};
+            SlimInst si{};
+            FatInst fi{};
+            uint32_t kind;
+            uint32_t xf_index = 0;
+            auto need_xf = [&]() {
+                Xf x{};
+                for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) x.m[4 * r + cc] = M.m[3 * r + cc];
+                xf_index = (uint32_t)xfs.size();
+                xfs.push_back(x);
+            };
+            if (o.kind == MRT_SPHERE) {
+                kind = K_SPHERE;
+                const float r = o.param[0];
+                si.a = make_float4(pos.x, pos.y, pos.z, 0.0f);
+                si.b = make_float4(r * r, 0.0f, 0.0f, 0.0f);
+                fi.A = make_float4(r, r * r, 0.0f, 0.0f);
+            } else if (o.kind == MRT_PLANE) {
+                kind = K_PLANE;
+                const H3 nraw = {o.param[0], o.param[1], o.param[2]};
+                const H3 nh = hnorm(nraw);  // Plane::intersect normalises, rt.rs:404
+                // t = -((o_l - pos).n^)/(d_l.n^) with o_l - pos = M(o - pos), d_l = M d  =>  n_w = M^T n^
+                const H3 nw = {M.m[0] * nh.x + M.m[3] * nh.y + M.m[6] * nh.z, M.m[1] * nh.x + M.m[4] * nh.y + M.m[7] * nh.z,
+                               M.m[2] * nh.x + M.m[5] * nh.y + M.m[8] * nh.z};
+                si.a = make_float4(nw.x, nw.y, nw.z, 0.0f);
+                si.b = make_float4(hdot(pos, nw), 0.0f, 0.0f, 0.0f);
+                const H3 ns = hnorm(hmul(M, nraw));  // Renderer::normal, rt.rs:786,792
+                fi.A = make_float4(ns.x, ns.y, ns.z, 0.0f);
+            } else if (o.kind == MRT_BOX) {
+                const H3 half = {0.5f * o.param[0], 0.5f * o.param[1], 0.5f * o.param[2]};
+                if (ident) {
+                    kind = K_BOX;
+                    si.a = make_float4(pos.x - half.x, pos.y - half.y, pos.z - half.z, 0.0f);
+                    si.b = make_float4(pos.x + half.x, pos.y + half.y, pos.z + half.z, 0.0f);
+                } else {
+                    kind = K_BOX_XF;
+                    need_xf();
+                    si.a = make_float4(pos.x, pos.y, pos.z, 0.0f);
+                    si.b = make_float4(half.x, half.y, half.z, 0.0f);
+                }
+                fi.A = make_float4(half.x, half.y, half.z, 0.0f);
+                fi.B = make_float4((1.0f / o.param[0]) * 2.0f, (1.0f / o.param[1]) * 2.0f, (1.0f / o.param[2]) * 2.0f, 0.0f);  // rt.rs:416
+            } else {
+                kind = K_MESH;
+                if (!ident) need_xf();
+                si.a = make_float4(pos.x, pos.y, pos.z, 0.0f);
+                si.b = make_float4(ident ? 0.0f : 1.0f, 0.0f, 0.0f, u2f(o.mesh));
+                fi.A = make_float4(u2f(meshes[o.mesh].first_tri), 0.0f, 0.0f, 0.0f);
+            }
+            if (xf_index > 0xffffffu) return fail(c, MRT_ERR_INVALID, "too many rotated instances");
+            si.a.w = u2f(kind | (xf_index << 8));
+            fi.pos_kind = make_float4(pos.x, pos.y, pos.z, u2f(kind | ((ident ? 1u : 0u) << 8)));
+            fi.m0 = make_float4(M.m[0], M.m[1], M.m[2], u2f(pack_ids(mt.tex, mt.rmap)));
+            fi.m1 = make_float4(M.m[3], M.m[4], M.m[5], u2f(pack_ids(mt.mmap, mt.gmap)));
+            fi.m2 = make_float4(M.m[6], M.m[7], M.m[8], u2f(pack_ids(mt.omap, mt.emap)));
+            fi.albedo_emit = make_float4(mt.albedo[0], mt.albedo[1], mt.albedo[2], mt.emit);
+            fi.rmgo = make_float4(mt.rough, mt.metal, mt.glass, mt.opacity);
+            slim.push_back(si);
+            fat.push_back(fi);
+            obj_inst.push_back(oi | (k << 16));
+        }
+    }
+    if (slim.size() > 0x7fffffffu) return fail(c, MRT_ERR_INVALID, "too many instances");
+
+    CK(cudaStreamSynchronize(c->stream));
+    CK(c->d_slim.upload(slim));
+    CK(c->d_xf.upload(xfs));
+    CK(c->d_fat.upload(fat));
+    CK(c->d_tex.upload(tex));
+    CK(c->d_texels.upload(texels));
+    CK(c->d_mesh.upload(meshes));
+    CK(c->d_leaf.upload(leaves));
+    CK(c->d_leaf_idx.upload(leaf_idx));
+    CK(c->d_tri.upload(tris));
+    CK(c->d_obj_inst.upload(obj_inst));
+
+    SceneCommon sc{};
+    sc.fat = c->d_fat.p; sc.tex = c->d_tex.p; sc.texels = c->d_texels.p;
+    sc.mesh = c->d_mesh.p; sc.leaf = c->d_leaf.p; sc.leaf_idx = c->d_leaf_idx.p; sc.tri = c->d_tri.p;
+    sc.n_inst = (uint32_t)slim.size();
+    sc.n_lights = s->n_lights;
+    for (int k = 0; k < 3; k++) { sc.sky[k] = s->sky_color[k]; sc.sky_tail[k] = s->sky_color[k] * s->sky_pwr; }
+    for (uint32_t i = 0; i < s->n_lights; i++) {
+        const mrt_light& l = s->lights[i];
+        if (l.kind > MRT_LIGHT_DIR) return fail(c, MRT_ERR_INVALID, "unknown light kind");
+        H3 v = {l.v[0], l.v[1], l.v[2]};
+        if (l.kind == MRT_LIGHT_DIR) { const H3 n = hnorm(v); v = {-n.x, -n.y, -n.z}; }  // rt.rs:977,1031: -dir.norm()
+        sc.light[i].v_kind = make_float4(v.x, v.y, v.z, u2f(l.kind));
+        sc.light[i].color_pwr = make_float4(l.color[0], l.color[1], l.color[2], l.pwr);
+    }
+    c->gscene.c = sc;
+    c->gscene.inst = c->d_slim.p;
+    c->gscene.xf = c->d_xf.p;
+    c->in_param = slim.size() <= MRT_PARAM_INST && xfs.size() <= MRT_PARAM_XF && !std::getenv("MRT_FORCE_GLOBAL_SCENE");
+    if (c->in_param) {
+        c->pscene->c = sc;
+        for (size_t i = 0; i < slim.size(); i++) c->pscene->inst[i] = slim[i];
+        for (size_t i = 0; i < xfs.size(); i++) c->pscene->xf[i] = xfs[i];
+    }
+    if (const char* f = std::getenv("MRT_FORCE_FEATURES")) feat |= (uint32_t)std::atoi(f) & F_ALL;
+    c->features = feat;
+    c->have_scene = true;
+    return mrt_reset(c);
+}
+
+int mrt_set_frame(mrt_ctx* c, const mrt_frame* f) {
+    if (!c || !f) return MRT_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    uint32_t nw, nh;
+    film_dims(*f, &nw, &nh);
+    if (nw == 0 || nh == 0 || f->res[0] == 0 || f->res[1] == 0) return fail(c, MRT_ERR_INVALID, "empty film");
+    if ((uint64_t)nw * nh > 0x7fffffffull) return fail(c, MRT_ERR_INVALID, "film too large");
+    CK(cudaStreamSynchronize(c->stream));
+    c->frame = *f;
+    c->nw = nw; c->nh = nh;
+    cudaError_t e = c->d_accum.alloc((size_t)nw * nh);
+    if (e != cudaSuccess) return cuda_fail(c, e, "accumulator allocation");
+    c->weights_ready = false;
+    c->have_frame = true;
+    return mrt_reset(c);
+}
+
+int mrt_set_rt(mrt_ctx* c, uint32_t bounce, float loss, uint64_t seed) {
+    if (!c) return MRT_ERR_INVALID;
+    if (bounce > 0x3fffffffu) return fail(c, MRT_ERR_INVALID, "bounce too large");
+    c->bounce = bounce; c->loss = loss; c->seed = seed;
+    return MRT_OK;
+}
+
+int mrt_set_partition(mrt_ctx* c, uint32_t rank, uint32_t world) {
+    if (!c) return MRT_ERR_INVALID;
+    if (world == 0 || rank >= world) return fail(c, MRT_ERR_INVALID, "bad partition");
+    c->rank = rank; c->world = world;
+    return MRT_OK;
+}
+
+int mrt_execute_async(mrt_ctx* c, uint32_t n_passes) {
+    if (!c) return MRT_ERR_INVALID;
+    if (!c->have_scene || !c->have_frame) return fail(c, MRT_ERR_STATE, "execute before set_scene/set_frame");
+    CK(cudaSetDevice(c->device));
+    FilmParams fp = make_film_params(c);
+    uint32_t left = n_passes;
+    while (left) {
+        const uint32_t n = std::min(left, c->spp_per_launch);
+        fp.sample0 = c->rank + c->passes * c->world;
+        fp.sample_stride = c->world;
+        fp.n_samples = n;
+        cudaError_t e = mrt_launch_path(c->features, c->in_param, c->pscene, &c->gscene, fp, c->stream);
+        if (e != cudaSuccess) return cuda_fail(c, e, "path kernel launch");
+        c->launches++;
+        c->passes += n;
+        c->passes_total += n;
+        left -= n;
+    }
+    return MRT_OK;
+}
+
+int mrt_sync(mrt_ctx* c) {
+    if (!c) return MRT_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return MRT_OK;
+}
+
+int mrt_execute(mrt_ctx* c, uint32_t n_passes, double* seconds) {
+    if (!c) return MRT_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    if (!c->have_scene || !c->have_frame) return fail(c, MRT_ERR_STATE, "execute before set_scene/set_frame");
+    CK(cudaEventRecord(c->ev0, c->stream));
+    int rc = mrt_execute_async(c, n_passes);
+    if (rc) return rc;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    if (seconds) {
+        float ms = 0.0f;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        *seconds = (double)ms * 1e-3;
+    }
+    return MRT_OK;
+}
+
+int mrt_film_size(mrt_ctx* c, uint32_t* nw, uint32_t* nh, uint32_t* passes) {
+    if (!c) return MRT_ERR_INVALID;
+    if (nw) *nw = c->nw;
+    if (nh) *nh = c->nh;
+    if (passes) *passes = c->passes_total;
+    return MRT_OK;
+}
+
+int mrt_accum(mrt_ctx* c, float* rgb, uint32_t* passes) {
+    if (!c || !rgb) return MRT_ERR_INVALID;
+    if (!c->have_frame) return fail(c, MRT_ERR_STATE, "accum before set_frame");
+    CK(cudaSetDevice(c->device));
+    const uint32_t npix = c->nw * c->nh;
+    CK(c->d_rgb.alloc((size_t)npix * 3));
+    CK(mrt_launch_unpack(c->d_accum.p, c->d_rgb.p, npix, c->stream));
+    c->launches++;
+    CK(cudaMemcpyAsync(rgb, c->d_rgb.p, (size_t)npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (passes) *passes = c->passes_total;
+    return MRT_OK;
+}
+
+int mrt_accum_device(mrt_ctx* c, void** dptr, size_t* n_floats, void** cuda_stream) {
+    if (!c) return MRT_ERR_INVALID;
+    if (!c->have_frame) return fail(c, MRT_ERR_STATE, "accum_device before set_frame");
+    if (dptr) *dptr = c->d_accum.p;
+    if (n_floats) *n_floats = (size_t)c->nw * c->nh * 4;
+    if (cuda_stream) *cuda_stream = (void*)c->stream;
+    return MRT_OK;
+}
+
+int mrt_set_stream(mrt_ctx* c, void* cuda_stream) {
+    if (!c) return MRT_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return MRT_OK;
+}
+
+int mrt_set_passes(mrt_ctx* c, uint32_t passes) {
+    if (!c) return MRT_ERR_INVALID;
+    c->passes_total = passes;
+    return MRT_OK;
+}
+
+static int tonemap_ss(mrt_ctx* c) {
+    if (!c->have_frame) return fail(c, MRT_ERR_STATE, "img before set_frame");
+    if (c->passes_total == 0) return fail(c, MRT_ERR_STATE, "img before any pass");
+    const uint32_t npix = c->nw * c->nh;
+    CK(c->d_ss.alloc((size_t)npix * 3));
+    const float inv_n = 1.0f / (float)c->passes_total;  // Vec3f / f32 = v * (1/n), lin.rs:296-302
+    CK(mrt_launch_tonemap(c->d_accum.p, c->d_ss.p, npix, inv_n, c->frame.gamma, c->frame.exp, c->stream));
+    c->launches++;
+    return MRT_OK;
+}
+
+int mrt_img_ss(mrt_ctx* c, uint8_t* rgb) {
+    if (!c || !rgb) return MRT_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    int rc = tonemap_ss(c);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(rgb, c->d_ss.p, (size_t)c->nw * c->nh * 3, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return MRT_OK;
+}
+
+int mrt_img(mrt_ctx* c, uint8_t* rgb) {
+    if (!c || !rgb) return MRT_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    int rc = tonemap_ss(c);
+    if (rc) return rc;
+    const uint32_t w = c->nw, h = c->nh, ow = c->frame.res[0], oh = c->frame.res[1];
+    if (ow == w && oh == h) {  // imageops::resize copies when the size is unchanged
+        CK(cudaMemcpyAsync(rgb, c->d_ss.p, (size_t)w * h * 3, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return MRT_OK;
+    }
+    if (!c->weights_ready) {
+        auto taps = [](uint32_t in_n, uint32_t out_n) {
+            const float ratio = (float)in_n / (float)out_n;
+            const float sr = ratio < 1.0f ? 1.0f : ratio;
+            return (uint32_t)std::ceil(2.0f * 3.0f * sr) + 3u;
+        };
+        c->taps_v = taps(h, oh);
+        c->taps_h = taps(w, ow);
+        CK(c->d_lv.alloc(oh)); CK(c->d_cv.alloc(oh)); CK(c->d_wv.alloc((size_t)oh * c->taps_v));
+        CK(c->d_lh.alloc(ow)); CK(c->d_ch.alloc(ow)); CK(c->d_wh.alloc((size_t)ow * c->taps_h));
+        CK(mrt_launch_lanczos_weights(h, oh, c->taps_v, c->d_lv.p, c->d_cv.p, c->d_wv.p, c->stream));
+        CK(mrt_launch_lanczos_weights(w, ow, c->taps_h, c->d_lh.p, c->d_ch.p, c->d_wh.p, c->stream));
+        c->launches += 2;
+        c->weights_ready = true;
+    }
+    CK(c->d_tmp.alloc((size_t)w * oh * 3));
+    CK(c->d_out.alloc((size_t)ow * oh * 3));
+    CK(mrt_launch_lanczos_vertical(c->d_ss.p, c->d_tmp.p, w, oh, c->taps_v, c->d_lv.p, c->d_cv.p, c->d_wv.p, c->stream));
+    CK(mrt_launch_lanczos_horizontal(c->d_tmp.p, c->d_out.p, w, ow, oh, c->taps_h, c->d_lh.p, c->d_ch.p, c->d_wh.p, c->stream));
+    c->launches += 2;
+    CK(cudaMemcpyAsync(rgb, c->d_out.p, (size_t)ow * oh * 3, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return MRT_OK;
+}
+
+int mrt_trace_primary(mrt_ctx* c, mrt_hit* out) {
+    if (!c || !out) return MRT_ERR_INVALID;
+    if (!c->have_scene || !c->have_frame) return fail(c, MRT_ERR_STATE, "trace_primary before set_scene/set_frame");
+    CK(cudaSetDevice(c->device));
+    const uint32_t npix = c->nw * c->nh;
+    CK(c->d_hits.alloc(npix));
+    FilmParams fp = make_film_params(c);
+    CK(mrt_launch_primary(c->gscene, fp, c->d_hits.p, c->d_obj_inst.p, c->stream));
+    c->launches++;
+    CK(cudaMemcpyAsync(out, c->d_hits.p, (size_t)npix * sizeof(mrt_hit), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return MRT_OK;
+}
+
+int mrt_launch_count(mrt_ctx* c, uint64_t* n) {
+    if (!c || !n) return MRT_ERR_INVALID;
+    *n = c->launches;
+    return MRT_OK;
+}
+
+int mrt_fp32_peak(mrt_ctx* c, double* tflops, double* seconds) {
+    if (!c || !tflops) return MRT_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c->device));
+    DevBuf<float> sink;
+    CK(sink.alloc(4));
+    const int blocks = prop.multiProcessorCount * 8;
+    const int iters = 16384;
+    CK(mrt_launch_fp32_peak(sink.p, blocks, 256, c->stream));  // warm-up
+    CK(cudaStreamSynchronize(c->stream));
+    double best = 0.0, best_s = 0.0;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(c->ev0, c->stream));
+        CK(mrt_launch_fp32_peak(sink.p, blocks, iters, c->stream));
+        CK(cudaEventRecord(c->ev1, c->stream));
+        CK(cudaEventSynchronize(c->ev1));
+        float ms = 0.0f;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        const double flops = (double)blocks * 256.0 * (double)iters * 64.0 * 2.0;
+        const double tf = flops / ((double)ms * 1e-3) / 1e12;
+        if (tf > best) { best = tf; best_s = (double)ms * 1e-3; }
+    }
+    c->launches += 4;
+    sink.release();
+    *tflops = best;
+    if (seconds) *seconds = best_s;
+    return MRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,451 @@
+// mrt_device.cuh — device-side scene layout and the per-ray building blocks of the
+// path-tracing hot path (sm_100a).  Reference semantics: /root/reference/src/rt.rs, lin.rs
+// (cited per function).  Design notes in DESIGN.md.
+//
+// Scene storage, two views of the same instance table:
+//   * SlimInst  (32 B/instance): what the closest-hit loop reads.  Every lane of a warp walks
+//     the same instance list, so these are warp-uniform loads: from the kernel-parameter
+//     constant bank (ParamView, scenes up to MRT_PARAM_INST instances; operands come straight
+//     from c[0][..]) or from global memory through L1 (GlobalView, any size).
+//   * FatInst   (128 B/instance = one L1 line): what a lane reads about the ONE instance it
+//     hit (transform, normal data, material); divergent, always global memory.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define MRT_E 0.0001f  // rt.rs:7
+
+enum : uint32_t {
+    K_SPHERE = 0, K_PLANE = 1, K_BOX = 2, K_BOX_XF = 3, K_MESH = 4,
+};
+// feature bits of a scene -> kernel specialisation
+enum : uint32_t {
+    F_LIGHTS = 1u,    // scene has lights: shadow rays + direct shading
+    F_TEX = 2u,       // some material has a texture map: uv + texel fetches
+    F_TRANSMIT = 4u,  // some material has opacity < 1 or an omap: exit hit + refraction
+    F_MESH = 8u,      // some object is a mesh
+    F_ALL = 15u
+};
+
+struct SlimInst {
+    // a.w = kind | xf_index << 8 (bits)
+    // sphere : a.xyz = centre            b.x = r^2
+    // plane  : a.xyz = n_w = M^T n^     b.x = pos . n_w          (t = -(o.n_w - b.x)/(d.n_w))
+    // box    : a.xyz = pos - half        b.xyz = pos + half        (identity transform)
+    // box_xf : a.xyz = pos               b.xyz = half              (+ xf[xf_index])
+    // mesh   : a.xyz = pos               b.w = mesh index (bits)   (+ xf[xf_index] if b.x != 0)
+    float4 a, b;
+};
+struct Xf { float m[12]; };  // rows of M = rot_y * look (rt.rs:726-727), padded to 3 x float4
+
+struct FatInst {
+    float4 pos_kind;   // pos.xyz, w = kind | identity << 8 (bits)
+    float4 A;          // sphere: (r, r^2, 0)   box: half sizes   plane: shading normal norm(M n)
+    float4 B;          // box: 2/size            w = obj index | inst-in-object index << 16? (see api)
+    float4 m0, m1, m2; // rows of M; .w = packed texture ids (tex|rmap<<16, mmap|gmap<<16, omap|emap<<16), 0xFFFF = none
+    float4 albedo_emit;
+    float4 rmgo;       // rough, metal, glass, opacity
+};
+static_assert(sizeof(FatInst) == 128, "FatInst must be one cache line");
+
+struct DLight { float4 v_kind; float4 color_pwr; };  // v.xyz (pos or unit -dir), w = kind bits ; color.rgb, pwr
+struct DTex { uint32_t w, h, first, has_dat; };      // texel offset into the float4 texel array
+struct DMeshLeaf { float4 lo, hi; };                  // leaf box relative to instance pos; lo.w = first index (bits), hi.w = count (bits)
+struct DMesh { uint32_t first_leaf, n_leaf, first_tri, n_tri; };
+struct DTri { float4 v0, e0, e1; };                   // v0, e0 = v1 - v0, e1 = v2 - v0 (object space, before + pos)
+
+#define MRT_PARAM_INST 448
+#define MRT_PARAM_XF 48
+#define MRT_MAX_LIGHTS 16
+
+struct SceneCommon {
+    const FatInst* fat;
+    const DTex* tex;
+    const float4* texels;
+    const DMesh* mesh;
+    const DMeshLeaf* leaf;
+    const uint32_t* leaf_idx;
+    const DTri* tri;
+    uint32_t n_inst, n_lights;
+    float sky[3];       // sky.color (primary miss, rt.rs:958)
+    float sky_tail[3];  // sky.color * sky.pwr (rt.rs:964)
+    DLight light[MRT_MAX_LIGHTS];
+};
+struct ParamScene {
+    SceneCommon c;
+    SlimInst inst[MRT_PARAM_INST];
+    Xf xf[MRT_PARAM_XF];
+};
+struct GlobalScene {
+    SceneCommon c;
+    const SlimInst* inst;
+    const Xf* xf;
+};
+
+struct FilmParams {
+    float4* accum;
+    uint32_t nw, nh;
+    uint32_t sample0, sample_stride, n_samples;  // this launch: global samples sample0 + j*stride
+    uint32_t key;
+    uint32_t max_bounce;
+    float keep;           // 1 - min(loss, 1)   (rt.rs:571)
+    float cam_pos[3];
+    float aprt, foc;
+    float cam_M[9];       // rot_y(cam.dir) * lookat(cam.dir, up)   (rt.rs:925-930)
+    float fw, fh;         // res * ssaa as f32 (rt.rs:938-939)
+    float fy;             // 1 / (2 tan(fov/2))  (rt.rs:902-906)
+};
+
+// ------------------------------------------------------------------ small vector helpers
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f3 mk(float x, float y, float z) { return {x, y, z}; }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ f3 operator-(f3 a) { return {-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ f3 operator*(f3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ f3 operator*(f3 a, f3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+__device__ __forceinline__ float dot(f3 a, f3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ f3 cross(f3 a, f3 b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ f3 fma3(f3 a, float s, f3 b) { return {fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z)}; }
+__device__ __forceinline__ f3 normalize(f3 a) { return a * rsqrtf(dot(a, a)); }  // lin.rs:64-66
+__device__ __forceinline__ f3 xyz(float4 v) { return {v.x, v.y, v.z}; }
+__device__ __forceinline__ f3 mulM(const float4& r0, const float4& r1, const float4& r2, f3 v) {
+    return {dot(xyz(r0), v), dot(xyz(r1), v), dot(xyz(r2), v)};
+}
+__device__ __forceinline__ f3 mulXf(const Xf& x, f3 v) {
+    return {fmaf(x.m[2], v.z, fmaf(x.m[1], v.y, x.m[0] * v.x)),
+            fmaf(x.m[6], v.z, fmaf(x.m[5], v.y, x.m[4] * v.x)),
+            fmaf(x.m[10], v.z, fmaf(x.m[9], v.y, x.m[8] * v.x))};
+}
+__device__ __forceinline__ float frcp(float x) { return __fdividef(1.0f, x); }
+
+// Box::intersect's reciprocal with the zero-division workaround, rt.rs:303-316
+__device__ __forceinline__ float rcp_fixed(float d) {
+    float m = frcp(d);
+    return (fabsf(m) == __int_as_float(0x7f800000)) ? (1.0f / MRT_E) : m;
+}
+__device__ __forceinline__ f3 rcp_fixed3(f3 d) { return {rcp_fixed(d.x), rcp_fixed(d.y), rcp_fixed(d.z)}; }
+
+// ------------------------------------------------------------------ RNG: pcg4d counter hash
+// (Jarzynski & Olano, JCGT 2020).  One call = the 4 uniforms of (pixel, sample, block);
+// identical to oracle/mrt_oracle.cpp rng_block so both consume the same numbers.
+__device__ __forceinline__ float4 rng_block(uint32_t pixel, uint32_t sample, uint32_t block, uint32_t key) {
+    uint32_t x = pixel * 1664525u + 1013904223u;
+    uint32_t y = sample * 1664525u + 1013904223u;
+    uint32_t z = block * 1664525u + 1013904223u;
+    uint32_t w = key * 1664525u + 1013904223u;
+    x += y * w; y += z * x; z += x * y; w += y * z;
+    x ^= x >> 16; y ^= y >> 16; z ^= z >> 16; w ^= w >> 16;
+    x += y * w; y += z * x; z += x * y; w += y * z;
+    const float s = 1.0f / 16777216.0f;
+    return make_float4((float)(x >> 8) * s, (float)(y >> 8) * s, (float)(z >> 8) * s, (float)(w >> 8) * s);
+}
+
+// ------------------------------------------------------------------ scene views
+struct ParamView {
+    const ParamScene& s;
+    __device__ __forceinline__ const SceneCommon& c() const { return s.c; }
+    __device__ __forceinline__ float4 ia(uint32_t i) const { return s.inst[i].a; }
+    __device__ __forceinline__ float4 ib(uint32_t i) const { return s.inst[i].b; }
+    __device__ __forceinline__ const Xf& xf(uint32_t i) const { return s.xf[i]; }
+};
+struct GlobalView {
+    const GlobalScene& s;
+    __device__ __forceinline__ const SceneCommon& c() const { return s.c; }
+    __device__ __forceinline__ float4 ia(uint32_t i) const { return __ldg(&s.inst[i].a); }
+    __device__ __forceinline__ float4 ib(uint32_t i) const { return __ldg(&s.inst[i].b); }
+    __device__ __forceinline__ const Xf& xf(uint32_t i) const { return s.xf[i]; }
+};
+
+// ------------------------------------------------------------------ primitive tests
+// Möller–Trumbore as written in rt.rs:361-398 (two-sided, |det| < E rejected, t >= 0).
+__device__ __forceinline__ bool tri_test(const DTri& tr, f3 o_rel /* ray.orig - pos */, f3 d, float* t_out) {
+    f3 e0 = xyz(tr.e0), e1 = xyz(tr.e1);
+    f3 p = cross(d, e1);
+    float det = dot(e0, p);
+    if (det < MRT_E && det > -MRT_E) return false;
+    float inv = frcp(det);
+    f3 t = o_rel - xyz(tr.v0);
+    float u = dot(t, p) * inv;
+    if (u < 0.0f || u > 1.0f) return false;
+    f3 q = cross(t, e0);
+    float v = dot(d, q) * inv;
+    if (v < 0.0f || (u + v) > 1.0f) return false;
+    float tt = dot(e1, q) * inv;
+    if (tt < 0.0f) return false;
+    *t_out = tt;
+    return true;
+}
+
+// Mesh leg of Renderer::intersect, rt.rs:740-772, over the flattened depth-3 octree: every
+// non-empty leaf the ray pierces contributes its triangle list (rt.rs:707-723); entry = first
+// minimum t, exit = last maximum t.  o_rel = object-space origin minus instance pos.
+__device__ __forceinline__ bool mesh_test(const SceneCommon& c, uint32_t mesh_id, f3 o_rel, f3 d,
+                                          float* t0, float* t1, int* i0, int* i1) {
+    const DMesh mh = c.mesh[mesh_id];
+    f3 m = rcp_fixed3(d);
+    f3 om = o_rel * m;
+    bool any = false;
+    float b0 = 0.f, b1 = 0.f;
+    int k0 = -1, k1 = -1;
+    for (uint32_t l = 0; l < mh.n_leaf; l++) {
+        const float4 lo = __ldg(&c.leaf[mh.first_leaf + l].lo);
+        const float4 hi = __ldg(&c.leaf[mh.first_leaf + l].hi);
+        float ax = fmaf(lo.x, m.x, -om.x), bx = fmaf(hi.x, m.x, -om.x);
+        float ay = fmaf(lo.y, m.y, -om.y), by = fmaf(hi.y, m.y, -om.y);
+        float az = fmaf(lo.z, m.z, -om.z), bz = fmaf(hi.z, m.z, -om.z);
+        float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+        float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+        if (tn > tf || tf < 0.0f) continue;
+        const uint32_t first = __float_as_uint(lo.w), cnt = __float_as_uint(hi.w);
+        for (uint32_t k = 0; k < cnt; k++) {
+            const uint32_t ti = __ldg(&c.leaf_idx[first + k]);
+            const DTri* tp = &c.tri[mh.first_tri + ti];
+            DTri tr;
+            tr.v0 = __ldg(&tp->v0); tr.e0 = __ldg(&tp->e0); tr.e1 = __ldg(&tp->e1);
+            float t;
+            if (!tri_test(tr, o_rel, d, &t)) continue;
+            if (!any) { b0 = b1 = t; k0 = k1 = (int)ti; any = true; continue; }
+            if (t < b0) { b0 = t; k0 = (int)ti; }
+            if (t >= b1) { b1 = t; k1 = (int)ti; }
+        }
+    }
+    if (!any) return false;
+    *t0 = b0; *t1 = b1; *i0 = k0; *i1 = k1;
+    return true;
+}
+
+struct HitRec {
+    float t0, t1;
+    int inst;        // flat instance index, -1 = miss
+    int tri0, tri1;  // mesh triangle of entry / exit
+};
+
+// RayTracer::closest_hit, rt.rs:867-898 (without the normals): brute force over the instance
+// list in declaration order, first minimum of t0 wins (strict <).  Box t0 may be negative
+// (rt.rs:327-331), sphere rejects t0 < 0 (rt.rs:353), plane needs t > 0 (rt.rs:407).
+// ANY = occlusion query for shadow rays (rt.rs:1036: "is there any hit at all").
+template <class V, uint32_t F, bool ANY, bool WANT_T1>
+__device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out) {
+    const uint32_t n = sc.c().n_inst;
+    const f3 m = rcp_fixed3(d);
+    const f3 om = o * m;
+    float best = __int_as_float(0x7f800000), best1 = 0.0f;
+    int bi = -1, bt0 = -1, bt1 = -1;
+    bool any = false;
+    for (uint32_t i = 0; i < n; i++) {
+        const float4 a = sc.ia(i);
+        const float4 b = sc.ib(i);
+        const uint32_t kw = __float_as_uint(a.w);
+        const uint32_t kind = kw & 0xffu;
+        float t0, t1 = 0.0f;
+        bool hit;
+        int tr0 = -1, tr1 = -1;
+        if (kind == K_BOX) {
+            // Box::intersect, rt.rs:299-333, slab form: a = pos - half, b = pos + half
+            float ax = fmaf(a.x, m.x, -om.x), bx = fmaf(b.x, m.x, -om.x);
+            float ay = fmaf(a.y, m.y, -om.y), by = fmaf(b.y, m.y, -om.y);
+            float az = fmaf(a.z, m.z, -om.z), bz = fmaf(b.z, m.z, -om.z);
+            t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+            t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+            hit = !(t0 > t1) && !(t1 < 0.0f);
+        } else if (kind == K_SPHERE) {
+            // Sphere::intersect, rt.rs:335-359 with a = d.d = 1 (directions are unit) in half-b form
+            f3 oc = o - xyz(a);
+            float hb = dot(oc, d);
+            float c = fmaf(oc.z, oc.z, fmaf(oc.y, oc.y, fmaf(oc.x, oc.x, -b.x)));
+            float disc = fmaf(hb, hb, -c);
+            float sq = sqrtf(fmaxf(disc, 0.0f));
+            t0 = -hb - sq;
+            t1 = sq - hb;
+            hit = (disc >= 0.0f) && (t0 >= 0.0f);
+        } else if (kind == K_PLANE) {
+            // Plane::intersect, rt.rs:400-412, with the instance transform folded into n_w
+            float num = dot(o, xyz(a)) - b.x;
+            float den = dot(d, xyz(a));
+            t0 = -num * frcp(den);
+            t1 = t0;
+            hit = t0 > 0.0f;
+        } else if (kind == K_BOX_XF) {
+            // rotated box: ray into object space (rt.rs:726-733), then the slab test about the origin
+            const Xf& x = sc.xf(kw >> 8);
+            f3 ol = mulXf(x, o - xyz(a));
+            f3 dl = mulXf(x, d);
+            f3 ml = rcp_fixed3(dl);
+            f3 nl = ol * ml;
+            f3 kl = mk(b.x * fabsf(ml.x), b.y * fabsf(ml.y), b.z * fabsf(ml.z));
+            t0 = fmaxf(fmaxf(-nl.x - kl.x, -nl.y - kl.y), -nl.z - kl.z);
+            t1 = fminf(fminf(kl.x - nl.x, kl.y - nl.y), kl.z - nl.z);
+            hit = !(t0 > t1) && !(t1 < 0.0f);
+        } else {
+            if constexpr ((F & F_MESH) != 0) {
+                f3 ol = o - xyz(a), dl = d;
+                if (b.x != 0.0f) {
+                    const Xf& x = sc.xf(kw >> 8);
+                    ol = mulXf(x, ol);
+                    dl = mulXf(x, d);
+                }
+                hit = mesh_test(sc.c(), __float_as_uint(b.w), ol, dl, &t0, &t1, &tr0, &tr1);
+            } else {
+                hit = false; t0 = 0.0f;
+            }
+        }
+        if constexpr (ANY) {
+            any |= hit;
+        } else {
+            if (hit && t0 < best) {
+                best = t0; bi = (int)i;
+                if constexpr (WANT_T1) best1 = t1;
+                if constexpr ((F & F_MESH) != 0) { bt0 = tr0; bt1 = tr1; }
+            }
+        }
+    }
+    if constexpr (ANY) return any;
+    out->t0 = best; out->t1 = best1; out->inst = bi; out->tri0 = bt0; out->tri1 = bt1;
+    return bi >= 0;
+}
+
+// ------------------------------------------------------------------ per-hit data of the winner
+struct Surf {
+    float4 pos_kind, A, B, m0, m1, m2;
+    __device__ __forceinline__ uint32_t kind() const { return __float_as_uint(pos_kind.w) & 0xffu; }
+    __device__ __forceinline__ bool identity() const { return (__float_as_uint(pos_kind.w) >> 8) & 1u; }
+};
+__device__ __forceinline__ void load_surf(const FatInst* f, Surf* s) {
+    s->pos_kind = __ldg(&f->pos_kind);
+    s->A = __ldg(&f->A);
+    s->B = __ldg(&f->B);
+    s->m0 = __ldg(&f->m0);
+    s->m1 = __ldg(&f->m1);
+    s->m2 = __ldg(&f->m2);
+}
+// object-space hit point minus instance pos: rot_y * (look * (hp - pos)), rt.rs:782
+__device__ __forceinline__ f3 to_local(const Surf& s, f3 hp) {
+    f3 r = hp - xyz(s.pos_kind);
+    return s.identity() ? r : mulM(s.m0, s.m1, s.m2, r);
+}
+// Box face of an object-space point: the axis whose |p_i| * (2/size_i) is nearest 1
+// (= largest); Box::normal (rt.rs:414-445) makes the same decision with +-1e-4 windows, and
+// differs only on edges (measure ~1e-4) and when its windows miss (normal = NaN there).
+__device__ __forceinline__ f3 box_face(const Surf& s, f3 pl, f3* p_out) {
+    f3 p = pl * xyz(s.B);
+    *p_out = p;
+    const float ax = fabsf(p.x), ay = fabsf(p.y), az = fabsf(p.z);
+    // Box::normal's windows [1-E, 1+E) / [-1-E, -1+E) and its if-chain, rt.rs:418-441: x before y,
+    // then — missing `else` at :435 — an independent z test that overrides.
+    const float lo = 1.0f - MRT_E, hi = 1.0f + MRT_E;
+    const bool wx = p.x >= 0.0f ? (ax >= lo && ax < hi) : (ax > lo && ax <= hi);
+    const bool wy = p.y >= 0.0f ? (ay >= lo && ay < hi) : (ay > lo && ay <= hi);
+    const bool wz = p.z >= 0.0f ? (az >= lo && az < hi) : (az > lo && az <= hi);
+    if (wz) return mk(0.f, 0.f, copysignf(1.0f, p.z));
+    if (wx) return mk(copysignf(1.0f, p.x), 0.f, 0.f);
+    if (wy) return mk(0.f, copysignf(1.0f, p.y), 0.f);
+    // no window matched: the reference normalises a zero vector (NaN normal, ~1e-7 of hits);
+    // take the nearest face instead of poisoning the path.
+    if (az >= ax && az >= ay) return mk(0.f, 0.f, copysignf(1.0f, p.z));
+    if (ax >= ay) return mk(copysignf(1.0f, p.x), 0.f, 0.f);
+    return mk(0.f, copysignf(1.0f, p.y), 0.f);
+}
+// Renderer::normal, rt.rs:776-793: kind normal of the object-space hit point, pushed through
+// the FORWARD transform again (rt.rs:792) and normalised.
+__device__ __forceinline__ f3 surf_normal(const SceneCommon& c, const Surf& s, f3 pl, int tri, uint32_t mesh_first_tri) {
+    const uint32_t k = s.kind();
+    f3 n;
+    if (k == K_PLANE) return xyz(s.A);  // precomputed norm(M n)
+    if (k == K_SPHERE) n = pl;
+    else if (k == K_MESH) {
+        const DTri* tp = &c.tri[mesh_first_tri + (uint32_t)tri];
+        n = cross(xyz(__ldg(&tp->e0)), xyz(__ldg(&tp->e1)));  // rt.rs:459-466
+    } else {
+        f3 p;
+        n = box_face(s, pl, &p);
+    }
+    if (!s.identity()) n = mulM(s.m0, s.m1, s.m2, n);
+    return normalize(n);
+}
+
+// UV impls, rt.rs:468-548, on the object-space point (pl = point - pos; plane uses the absolute
+// object-space point, rt.rs:529-541).
+__device__ __forceinline__ float2 surf_uv(const Surf& s, f3 pl) {
+    const uint32_t k = s.kind();
+    if (k == K_SPHERE) {
+        f3 v = normalize(pl);
+        return make_float2(0.5f + 0.5f * atan2f(v.x, -v.y) * 0.31830988618379067154f, 0.5f - 0.5f * v.z);
+    }
+    if (k == K_PLANE) {
+        f3 h = pl + xyz(s.pos_kind);
+        float x = h.x + 0.5f; x = x - truncf(x); if (x < 0.0f) x = 1.0f + x;
+        float y = h.y + 0.5f; y = y - truncf(y); if (y < 0.0f) y = 1.0f + y;
+        return make_float2(x, y);
+    }
+    if (k == K_BOX || k == K_BOX_XF) {
+        f3 p = pl * xyz(s.B);
+        const float pl_ = 1.0f - MRT_E, ph = 1.0f + MRT_E, nl = -1.0f - MRT_E, nh = -1.0f + MRT_E;
+        const float th = 1.0f / 3.0f;
+        // same chain and priorities as rt.rs:475-514 (x and y faces return before z is looked at)
+        if (p.x >= pl_ && p.x < ph) return make_float2((0.5f + 0.5f * p.y) * 0.25f + 0.5f, (0.5f - 0.5f * p.z) * th + th);
+        if (p.x >= nl && p.x < nh) return make_float2((0.5f - 0.5f * p.y) * 0.25f, (0.5f - 0.5f * p.z) * th + th);
+        if (p.y >= pl_ && p.y < ph) return make_float2((0.5f - 0.5f * p.x) * 0.25f + 0.75f, (0.5f - 0.5f * p.z) * th + th);
+        if (p.y >= nl && p.y < nh) return make_float2((0.5f + 0.5f * p.x) * 0.25f + 0.25f, (0.5f - 0.5f * p.z) * th + th);
+        if (p.z >= pl_ && p.z < ph) return make_float2((0.5f + 0.5f * p.x) * 0.25f + 0.25f, (0.5f - 0.5f * p.y) * th);
+        if (p.z >= nl && p.z < nh) return make_float2((0.5f + 0.5f * p.x) * 0.25f + 0.25f, (0.5f + 0.5f * p.y) * th + 2.0f * th);
+        return make_float2(0.0f, 0.0f);
+    }
+    return make_float2(0.0f, 0.0f);
+}
+
+// Texture::get_color, rt.rs:618-628: nearest texel, truncating casts, linear index x + y*w
+// (u == 1 runs into the next row, as in the reference); the index is clamped to the last
+// texel where the reference would panic.
+__device__ __forceinline__ float4 tex_fetch(const SceneCommon& c, uint32_t id, float2 uv) {
+    const DTex t = c.tex[id];
+    if (!t.has_dat) return make_float4(0.f, 0.f, 0.f, 0.f);
+    float fx = uv.x * (float)t.w, fy = uv.y * (float)t.h;
+    // Rust `as usize`: NaN/negative -> 0, saturating
+    unsigned long long x = (fx > 0.0f) ? (fx >= 1.8446744e19f ? ~0ull : (unsigned long long)fx) : 0ull;
+    unsigned long long y = (fy > 0.0f) ? (fy >= 1.8446744e19f ? ~0ull : (unsigned long long)fy) : 0ull;
+    const unsigned long long n = (unsigned long long)t.w * t.h;
+    unsigned long long idx = (y >= n || x >= n) ? n - 1 : y * t.w + x;
+    if (idx >= n) idx = n - 1;
+    return __ldg(&c.texels[t.first + (uint32_t)idx]);
+}
+
+struct Mat {
+    f3 color;
+    float rough, metal, glass, opacity, emit;
+    float metal_raw;  // Ray::reflect tests the raw field (rt.rs:564), not the mmap
+};
+// material getters, rt.rs:811-863, all maps fetched at the same uv
+template <uint32_t F>
+__device__ __forceinline__ void load_mat(const SceneCommon& c, const FatInst* f, const Surf& s, f3 pl, Mat* m) {
+    const float4 ae = __ldg(&f->albedo_emit);
+    const float4 r = __ldg(&f->rmgo);
+    m->color = xyz(ae); m->emit = ae.w;
+    m->rough = r.x; m->metal = r.y; m->glass = r.z; m->opacity = r.w; m->metal_raw = r.y;
+    if constexpr ((F & F_TEX) != 0) {
+        const uint32_t t0 = __float_as_uint(s.m0.w), t1 = __float_as_uint(s.m1.w), t2 = __float_as_uint(s.m2.w);
+        if ((t0 & t1 & t2) != 0xffffffffu) {
+            const float2 uv = surf_uv(s, pl);
+            if ((t0 & 0xffffu) != 0xffffu) m->color = m->color * xyz(tex_fetch(c, t0 & 0xffffu, uv));
+            if ((t0 >> 16) != 0xffffu) m->rough = tex_fetch(c, t0 >> 16, uv).x;
+            if ((t1 & 0xffffu) != 0xffffu) m->metal = tex_fetch(c, t1 & 0xffffu, uv).x;
+            if ((t1 >> 16) != 0xffffu) m->glass = tex_fetch(c, t1 >> 16, uv).x;
+            if ((t2 & 0xffffu) != 0xffffu) m->opacity = tex_fetch(c, t2 & 0xffffu, uv).x;
+            if ((t2 >> 16) != 0xffffu) m->emit = tex_fetch(c, t2 >> 16, uv).x;
+        }
+    }
+}
+
+// RayTracer::rand, rt.rs:996-1007: n + r * (uniform point on the unit sphere), normalised.
+// th = acos(1-2u1) => cos th = 1-2u1, sin th = sqrt(1 - cos^2): same distribution, no acos.
+__device__ __forceinline__ f3 rand_normal(f3 n, float r, float u1, float u2) {
+    float z = 1.0f - 2.0f * u1;
+    float st = sqrtf(fmaxf(0.0f, fmaf(-z, z, 1.0f)));
+    float sp, cp;
+    __sincosf(u2 * 6.283185307179586f, &sp, &cp);
+    f3 v = mk(st * cp, st * sp, z);
+    return normalize(fma3(v, r, n));
+}
+__device__ __forceinline__ f3 reflect3(f3 v, f3 n) { return fma3(n, -2.0f * dot(v, n), v); }  // lin.rs:68-70

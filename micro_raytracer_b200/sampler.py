@@ -60,6 +60,7 @@ def declare(lib, prefix: str = "mrt_"):
         fn("sync", P)
         fn("accum_device", P, C.POINTER(P), C.POINTER(C.c_size_t), C.POINTER(P))
         fn("set_passes", P, u32)
+        fn("set_stream", P, P)
         fn("launch_count", P, C.POINTER(u64))
         fn("fp32_peak", P, C.POINTER(C.c_double), C.POINTER(C.c_double))
     return lib
@@ -224,6 +225,10 @@ class Sampler:
         p, n, s = C.c_void_p(), C.c_size_t(), C.c_void_p()
         self._check(self._lib.mrt_accum_device(self._ctx, C.byref(p), C.byref(n), C.byref(s)))
         return _DeviceArray(p.value, n.value, self), s.value
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        """Queue this sampler's work on a caller-owned stream (e.g. torch's current stream)."""
+        self._check(self._lib.mrt_set_stream(self._ctx, C.c_void_p(cuda_stream or 0)))
 
     def set_passes(self, passes: int):
         self._check(self._lib.mrt_set_passes(self._ctx, int(passes)))

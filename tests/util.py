@@ -1,0 +1,45 @@
+"""Shared helpers for the parity tests."""
+import os
+
+import numpy as np
+
+import micro_raytracer_b200 as mrt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCENES = os.path.join(ROOT, "tests", "golden", "scenes")
+REF_RENDERS = os.path.join(ROOT, "tests", "golden", "ref_renders")
+
+
+def load(name, res=None, ssaa=None, **rt):
+    r = mrt.load_render(os.path.join(SCENES, name + ".json"))
+    if res is not None:
+        r.frame.res = tuple(res)
+    if ssaa is not None:
+        r.frame.ssaa = float(ssaa)
+    for k, v in rt.items():
+        setattr(r.rt, k, v)
+    return r
+
+
+def png(name):
+    from PIL import Image
+    return np.asarray(Image.open(os.path.join(REF_RENDERS, name)).convert("RGB"))
+
+
+def block_mean(a, b=8):
+    h, w = a.shape[0] // b * b, a.shape[1] // b * b
+    a = a[:h, :w].astype(np.float64)
+    return a.reshape(h // b, b, w // b, b, -1).mean(axis=(1, 3))
+
+
+def psnr(a, b, peak=255.0):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return float("inf") if mse == 0 else 10.0 * np.log10(peak * peak / mse)
+
+
+def have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:  # noqa: BLE001
+        return False
