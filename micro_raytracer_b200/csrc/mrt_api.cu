@@ -93,8 +93,8 @@ struct mrt_ctx {
     uint32_t features = 0;
     ParamScene* pscene = nullptr;  // host staging copies of the kernel-parameter structs
     GlobalScene gscene{};
-    DevBuf<SlimInst> d_slim;
-    DevBuf<Xf> d_xf;
+    DevBuf<SlimInst> d_slim[K_NKIND];
+    DevBuf<Xf> d_bxf_m, d_mesh_m;
     DevBuf<FatInst> d_fat;
     DevBuf<DTex> d_tex;
     DevBuf<float4> d_texels;
@@ -248,7 +248,8 @@ void mrt_destroy(mrt_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    c->d_slim.release(); c->d_xf.release(); c->d_fat.release(); c->d_tex.release(); c->d_texels.release();
+    for (auto& b : c->d_slim) b.release();
+    c->d_bxf_m.release(); c->d_mesh_m.release(); c->d_fat.release(); c->d_tex.release(); c->d_texels.release();
     c->d_mesh.release(); c->d_leaf.release(); c->d_leaf_idx.release(); c->d_tri.release(); c->d_obj_inst.release();
     c->d_accum.release(); c->d_ss.release(); c->d_out.release(); c->d_tmp.release(); c->d_rgb.release();
     c->d_wv.release(); c->d_wh.release(); c->d_lv.release(); c->d_cv.release(); c->d_lh.release(); c->d_ch.release();
@@ -322,11 +323,11 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
             tris.push_back(d);
         }
     }
-    // instances
-    std::vector<SlimInst> slim;
-    std::vector<FatInst> fat;
-    std::vector<Xf> xfs;
-    std::vector<uint32_t> obj_inst;
+    // instances, grouped by kind (declaration order inside a kind)
+    std::vector<SlimInst> by_kind[K_NKIND];
+    std::vector<FatInst> fat_k[K_NKIND];
+    std::vector<uint32_t> oi_k[K_NKIND];
+    std::vector<Xf> bxf_m, mesh_m;
     for (uint32_t oi = 0; oi < s->n_objects; oi++) {
         const mrt_object& o = s->objects[oi];
         const mrt_material& mt = o.mat;
@@ -358,19 +359,14 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
             SlimInst si{};
             FatInst fi{};
             uint32_t kind;
-            uint32_t xf_index = 0;
-            auto need_xf = [&]() {
-                Xf x{};
-                for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) x.m[4 * r + cc] = M.m[3 * r + cc];
-                xf_index = (uint32_t)xfs.size();
-                xfs.push_back(x);
-            };
+            Xf x{};
+            for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) x.m[4 * r + cc] = M.m[3 * r + cc];
             if (o.kind == MRT_SPHERE) {
                 kind = K_SPHERE;
                 const float r = o.param[0];
                 si.a = make_float4(pos.x, pos.y, pos.z, 0.0f);
                 si.b = make_float4(r * r, 0.0f, 0.0f, 0.0f);
-                fi.A = make_float4(r, r * r, 0.0f, 0.0f);
+                fi.A = make_float4(1.0f / r, r, 0.0f, 0.0f);
             } else if (o.kind == MRT_PLANE) {
                 kind = K_PLANE;
                 const H3 nraw = {o.param[0], o.param[1], o.param[2]};
@@ -383,44 +379,44 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
                 const H3 ns = hnorm(hmul(M, nraw));  // Renderer::normal, rt.rs:786,792
                 fi.A = make_float4(ns.x, ns.y, ns.z, 0.0f);
             } else if (o.kind == MRT_BOX) {
-                const H3 half = {0.5f * o.param[0], 0.5f * o.param[1], 0.5f * o.param[2]};
-                if (ident) {
-                    kind = K_BOX;
-                    si.a = make_float4(pos.x - half.x, pos.y - half.y, pos.z - half.z, 0.0f);
-                    si.b = make_float4(pos.x + half.x, pos.y + half.y, pos.z + half.z, 0.0f);
-                } else {
-                    kind = K_BOX_XF;
-                    need_xf();
-                    si.a = make_float4(pos.x, pos.y, pos.z, 0.0f);
-                    si.b = make_float4(half.x, half.y, half.z, 0.0f);
-                }
-                fi.A = make_float4(half.x, half.y, half.z, 0.0f);
-                fi.B = make_float4((1.0f / o.param[0]) * 2.0f, (1.0f / o.param[1]) * 2.0f, (1.0f / o.param[2]) * 2.0f, 0.0f);  // rt.rs:416
+                kind = ident ? K_BOX : K_BOX_XF;
+                si.a = make_float4(pos.x, pos.y, pos.z, 0.0f);
+                si.b = make_float4(0.5f * o.param[0], 0.5f * o.param[1], 0.5f * o.param[2], 0.0f);
+                if (!ident) bxf_m.push_back(x);
+                fi.A = make_float4((1.0f / o.param[0]) * 2.0f, (1.0f / o.param[1]) * 2.0f, (1.0f / o.param[2]) * 2.0f, 0.0f);  // rt.rs:416
             } else {
                 kind = K_MESH;
-                if (!ident) need_xf();
                 si.a = make_float4(pos.x, pos.y, pos.z, 0.0f);
-                si.b = make_float4(ident ? 0.0f : 1.0f, 0.0f, 0.0f, u2f(o.mesh));
+                si.b = make_float4(u2f(ident ? 0u : 1u), u2f(o.mesh), 0.0f, 0.0f);
+                mesh_m.push_back(x);
                 fi.A = make_float4(u2f(meshes[o.mesh].first_tri), 0.0f, 0.0f, 0.0f);
             }
-            if (xf_index > 0xffffffu) return fail(c, MRT_ERR_INVALID, "too many rotated instances");
-            si.a.w = u2f(kind | (xf_index << 8));
-            fi.pos_kind = make_float4(pos.x, pos.y, pos.z, u2f(kind | ((ident ? 1u : 0u) << 8)));
+            fi.P = make_float4(pos.x, pos.y, pos.z, u2f(kind | (ident ? FAT_IDENT : 0u) | (textured ? FAT_TEX : 0u)));
             fi.m0 = make_float4(M.m[0], M.m[1], M.m[2], u2f(pack_ids(mt.tex, mt.rmap)));
             fi.m1 = make_float4(M.m[3], M.m[4], M.m[5], u2f(pack_ids(mt.mmap, mt.gmap)));
             fi.m2 = make_float4(M.m[6], M.m[7], M.m[8], u2f(pack_ids(mt.omap, mt.emap)));
-            fi.albedo_emit = make_float4(mt.albedo[0], mt.albedo[1], mt.albedo[2], mt.emit);
-            fi.rmgo = make_float4(mt.rough, mt.metal, mt.glass, mt.opacity);
-            slim.push_back(si);
-            fat.push_back(fi);
-            obj_inst.push_back(oi | (k << 16));
+            fi.C = make_float4(mt.albedo[0], mt.albedo[1], mt.albedo[2], mt.emit);
+            fi.R = make_float4(mt.rough, mt.metal, mt.glass, mt.opacity);
+            by_kind[kind].push_back(si);
+            fat_k[kind].push_back(fi);
+            oi_k[kind].push_back(oi | (k << 16));
         }
     }
-    if (slim.size() > 0x7fffffffu) return fail(c, MRT_ERR_INVALID, "too many instances");
+    std::vector<FatInst> fat;
+    std::vector<uint32_t> obj_inst;
+    uint32_t first[K_NKIND], cnt[K_NKIND];
+    for (uint32_t k = 0; k < K_NKIND; k++) {
+        first[k] = (uint32_t)fat.size();
+        cnt[k] = (uint32_t)by_kind[k].size();
+        fat.insert(fat.end(), fat_k[k].begin(), fat_k[k].end());
+        obj_inst.insert(obj_inst.end(), oi_k[k].begin(), oi_k[k].end());
+    }
+    if (fat.size() > 0x7fffffffu) return fail(c, MRT_ERR_INVALID, "too many instances");
 
     CK(cudaStreamSynchronize(c->stream));
-    CK(c->d_slim.upload(slim));
-    CK(c->d_xf.upload(xfs));
+    for (uint32_t k = 0; k < K_NKIND; k++) CK(c->d_slim[k].upload(by_kind[k]));
+    CK(c->d_bxf_m.upload(bxf_m));
+    CK(c->d_mesh_m.upload(mesh_m));
     CK(c->d_fat.upload(fat));
     CK(c->d_tex.upload(tex));
     CK(c->d_texels.upload(texels));
@@ -433,8 +429,9 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     SceneCommon sc{};
     sc.fat = c->d_fat.p; sc.tex = c->d_tex.p; sc.texels = c->d_texels.p;
     sc.mesh = c->d_mesh.p; sc.leaf = c->d_leaf.p; sc.leaf_idx = c->d_leaf_idx.p; sc.tri = c->d_tri.p;
-    sc.n_inst = (uint32_t)slim.size();
+    sc.n_inst = (uint32_t)fat.size();
     sc.n_lights = s->n_lights;
+    for (uint32_t k = 0; k < K_NKIND; k++) { sc.first[k] = first[k]; sc.cnt[k] = cnt[k]; }
     for (int k = 0; k < 3; k++) { sc.sky[k] = s->sky_color[k]; sc.sky_tail[k] = s->sky_color[k] * s->sky_pwr; }
     for (uint32_t i = 0; i < s->n_lights; i++) {
         const mrt_light& l = s->lights[i];
@@ -445,13 +442,21 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
         sc.light[i].color_pwr = make_float4(l.color[0], l.color[1], l.color[2], l.pwr);
     }
     c->gscene.c = sc;
-    c->gscene.inst = c->d_slim.p;
-    c->gscene.xf = c->d_xf.p;
-    c->in_param = slim.size() <= MRT_PARAM_INST && xfs.size() <= MRT_PARAM_XF && !std::getenv("MRT_FORCE_GLOBAL_SCENE");
+    c->gscene.box = c->d_slim[K_BOX].p; c->gscene.sph = c->d_slim[K_SPHERE].p; c->gscene.pln = c->d_slim[K_PLANE].p;
+    c->gscene.bxf = c->d_slim[K_BOX_XF].p; c->gscene.bxf_m = c->d_bxf_m.p;
+    c->gscene.mesh = c->d_slim[K_MESH].p; c->gscene.mesh_m = c->d_mesh_m.p;
+    c->in_param = cnt[K_BOX] <= MRT_PB && cnt[K_SPHERE] <= MRT_PS && cnt[K_PLANE] <= MRT_PP && cnt[K_BOX_XF] <= MRT_PX &&
+                  cnt[K_MESH] <= MRT_PM && !std::getenv("MRT_FORCE_GLOBAL_SCENE");
     if (c->in_param) {
-        c->pscene->c = sc;
-        for (size_t i = 0; i < slim.size(); i++) c->pscene->inst[i] = slim[i];
-        for (size_t i = 0; i < xfs.size(); i++) c->pscene->xf[i] = xfs[i];
+        ParamScene& ps = *c->pscene;
+        ps.c = sc;
+        std::copy(by_kind[K_BOX].begin(), by_kind[K_BOX].end(), ps.box);
+        std::copy(by_kind[K_SPHERE].begin(), by_kind[K_SPHERE].end(), ps.sph);
+        std::copy(by_kind[K_PLANE].begin(), by_kind[K_PLANE].end(), ps.pln);
+        std::copy(by_kind[K_BOX_XF].begin(), by_kind[K_BOX_XF].end(), ps.bxf);
+        std::copy(bxf_m.begin(), bxf_m.end(), ps.bxf_m);
+        std::copy(by_kind[K_MESH].begin(), by_kind[K_MESH].end(), ps.mesh);
+        std::copy(mesh_m.begin(), mesh_m.end(), ps.mesh_m);
     }
     if (const char* f = std::getenv("MRT_FORCE_FEATURES")) feat |= (uint32_t)std::atoi(f) & F_ALL;
     c->features = feat;

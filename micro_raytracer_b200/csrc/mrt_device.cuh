@@ -16,7 +16,7 @@
 #define MRT_E 0.0001f  // rt.rs:7
 
 enum : uint32_t {
-    K_SPHERE = 0, K_PLANE = 1, K_BOX = 2, K_BOX_XF = 3, K_MESH = 4,
+    K_BOX = 0, K_SPHERE = 1, K_PLANE = 2, K_BOX_XF = 3, K_MESH = 4, K_NKIND = 5
 };
 // feature bits of a scene -> kernel specialisation
 enum : uint32_t {
@@ -27,24 +27,26 @@ enum : uint32_t {
     F_ALL = 15u
 };
 
+// The closest-hit loops walk one table per primitive kind (no per-instance dispatch), each in
+// declaration order; the FatInst table is sorted the same way (kind, then declaration order).
 struct SlimInst {
-    // a.w = kind | xf_index << 8 (bits)
+    // box    : a.xyz = centre            b.xyz = half sizes        (identity transform)
     // sphere : a.xyz = centre            b.x = r^2
     // plane  : a.xyz = n_w = M^T n^     b.x = pos . n_w          (t = -(o.n_w - b.x)/(d.n_w))
-    // box    : a.xyz = pos - half        b.xyz = pos + half        (identity transform)
-    // box_xf : a.xyz = pos               b.xyz = half              (+ xf[xf_index])
-    // mesh   : a.xyz = pos               b.w = mesh index (bits)   (+ xf[xf_index] if b.x != 0)
+    // box_xf : a.xyz = pos               b.xyz = half              (+ its Xf at the same index)
+    // mesh   : a.xyz = pos               b.x = 1 if rotated (bits), b.y = mesh index (bits)   (+ its Xf)
     float4 a, b;
 };
 struct Xf { float m[12]; };  // rows of M = rot_y * look (rt.rs:726-727), padded to 3 x float4
 
+enum : uint32_t { FAT_IDENT = 0x100u, FAT_TEX = 0x200u };
 struct FatInst {
-    float4 pos_kind;   // pos.xyz, w = kind | identity << 8 (bits)
-    float4 A;          // sphere: (r, r^2, 0)   box: half sizes   plane: shading normal norm(M n)
-    float4 B;          // box: 2/size            w = obj index | inst-in-object index << 16? (see api)
+    float4 P;          // pos.xyz, w = kind | FAT_IDENT | FAT_TEX (bits)
+    float4 A;          // box: 2/size   sphere: (1/r, r, 0)   plane: shading normal norm(M n)   mesh: x = first_tri (bits)
+    float4 C;          // albedo.rgb, emit
+    float4 R;          // rough, metal, glass, opacity
     float4 m0, m1, m2; // rows of M; .w = packed texture ids (tex|rmap<<16, mmap|gmap<<16, omap|emap<<16), 0xFFFF = none
-    float4 albedo_emit;
-    float4 rmgo;       // rough, metal, glass, opacity
+    float4 S;          // spare
 };
 static_assert(sizeof(FatInst) == 128, "FatInst must be one cache line");
 
@@ -54,12 +56,16 @@ struct DMeshLeaf { float4 lo, hi; };                  // leaf box relative to in
 struct DMesh { uint32_t first_leaf, n_leaf, first_tri, n_tri; };
 struct DTri { float4 v0, e0, e1; };                   // v0, e0 = v1 - v0, e1 = v2 - v0 (object space, before + pos)
 
-#define MRT_PARAM_INST 448
-#define MRT_PARAM_XF 48
+// capacities of the kernel-parameter scene (constant bank); larger scenes use GlobalScene
+#define MRT_PB 160  // axis-aligned boxes
+#define MRT_PS 96   // spheres
+#define MRT_PP 32   // planes
+#define MRT_PX 24   // rotated boxes
+#define MRT_PM 8    // mesh instances
 #define MRT_MAX_LIGHTS 16
 
 struct SceneCommon {
-    const FatInst* fat;
+    const FatInst* fat;   // sorted by (kind, declaration order): index = first[kind] + k
     const DTex* tex;
     const float4* texels;
     const DMesh* mesh;
@@ -67,19 +73,32 @@ struct SceneCommon {
     const uint32_t* leaf_idx;
     const DTri* tri;
     uint32_t n_inst, n_lights;
+    uint32_t cnt[K_NKIND];    // instances per kind
+    uint32_t first[K_NKIND];  // FatInst index of the kind's first instance
     float sky[3];       // sky.color (primary miss, rt.rs:958)
     float sky_tail[3];  // sky.color * sky.pwr (rt.rs:964)
     DLight light[MRT_MAX_LIGHTS];
 };
 struct ParamScene {
     SceneCommon c;
-    SlimInst inst[MRT_PARAM_INST];
-    Xf xf[MRT_PARAM_XF];
+    SlimInst box[MRT_PB];
+    SlimInst sph[MRT_PS];
+    SlimInst pln[MRT_PP];
+    SlimInst bxf[MRT_PX];
+    Xf bxf_m[MRT_PX];
+    SlimInst mesh[MRT_PM];
+    Xf mesh_m[MRT_PM];
 };
+static_assert(sizeof(ParamScene) + 256 < 32764, "kernel parameters are limited to 32764 bytes");
 struct GlobalScene {
     SceneCommon c;
-    const SlimInst* inst;
-    const Xf* xf;
+    const SlimInst* box;
+    const SlimInst* sph;
+    const SlimInst* pln;
+    const SlimInst* bxf;
+    const Xf* bxf_m;
+    const SlimInst* mesh;
+    const Xf* mesh_m;
 };
 
 struct FilmParams {
@@ -145,18 +164,29 @@ __device__ __forceinline__ float4 rng_block(uint32_t pixel, uint32_t sample, uin
 
 // ------------------------------------------------------------------ scene views
 struct ParamView {
+    static constexpr bool kParam = true;
     const ParamScene& s;
     __device__ __forceinline__ const SceneCommon& c() const { return s.c; }
-    __device__ __forceinline__ float4 ia(uint32_t i) const { return s.inst[i].a; }
-    __device__ __forceinline__ float4 ib(uint32_t i) const { return s.inst[i].b; }
-    __device__ __forceinline__ const Xf& xf(uint32_t i) const { return s.xf[i]; }
+    __device__ __forceinline__ SlimInst box(uint32_t k) const { return s.box[k]; }
+    __device__ __forceinline__ SlimInst sph(uint32_t k) const { return s.sph[k]; }
+    __device__ __forceinline__ SlimInst pln(uint32_t k) const { return s.pln[k]; }
+    __device__ __forceinline__ SlimInst bxf(uint32_t k) const { return s.bxf[k]; }
+    __device__ __forceinline__ const Xf& bxf_m(uint32_t k) const { return s.bxf_m[k]; }
+    __device__ __forceinline__ SlimInst mesh(uint32_t k) const { return s.mesh[k]; }
+    __device__ __forceinline__ const Xf& mesh_m(uint32_t k) const { return s.mesh_m[k]; }
 };
+__device__ __forceinline__ SlimInst ldg_slim(const SlimInst* p) { return {__ldg(&p->a), __ldg(&p->b)}; }
 struct GlobalView {
+    static constexpr bool kParam = false;
     const GlobalScene& s;
     __device__ __forceinline__ const SceneCommon& c() const { return s.c; }
-    __device__ __forceinline__ float4 ia(uint32_t i) const { return __ldg(&s.inst[i].a); }
-    __device__ __forceinline__ float4 ib(uint32_t i) const { return __ldg(&s.inst[i].b); }
-    __device__ __forceinline__ const Xf& xf(uint32_t i) const { return s.xf[i]; }
+    __device__ __forceinline__ SlimInst box(uint32_t k) const { return ldg_slim(s.box + k); }
+    __device__ __forceinline__ SlimInst sph(uint32_t k) const { return ldg_slim(s.sph + k); }
+    __device__ __forceinline__ SlimInst pln(uint32_t k) const { return ldg_slim(s.pln + k); }
+    __device__ __forceinline__ SlimInst bxf(uint32_t k) const { return ldg_slim(s.bxf + k); }
+    __device__ __forceinline__ const Xf& bxf_m(uint32_t k) const { return s.bxf_m[k]; }
+    __device__ __forceinline__ SlimInst mesh(uint32_t k) const { return ldg_slim(s.mesh + k); }
+    __device__ __forceinline__ const Xf& mesh_m(uint32_t k) const { return s.mesh_m[k]; }
 };
 
 // ------------------------------------------------------------------ primitive tests
@@ -219,151 +249,201 @@ __device__ __forceinline__ bool mesh_test(const SceneCommon& c, uint32_t mesh_id
 
 struct HitRec {
     float t0, t1;
-    int inst;        // flat instance index, -1 = miss
+    int inst;        // declaration-order instance index, -1 = miss
     int tri0, tri1;  // mesh triangle of entry / exit
 };
 
-// RayTracer::closest_hit, rt.rs:867-898 (without the normals): brute force over the instance
-// list in declaration order, first minimum of t0 wins (strict <).  Box t0 may be negative
-// (rt.rs:327-331), sphere rejects t0 < 0 (rt.rs:353), plane needs t > 0 (rt.rs:407).
+// RayTracer::closest_hit, rt.rs:867-898 (without the normals): brute force over every
+// instance; the first minimum of t0 wins (rt.rs:872).  Box t0 may be negative (rt.rs:327-331),
+// sphere rejects t0 < 0 (rt.rs:353), plane needs t > 0 (rt.rs:407).
 // ANY = occlusion query for shadow rays (rt.rs:1036: "is there any hit at all").
-template <class V, uint32_t F, bool ANY, bool WANT_T1>
-__device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out) {
-    const uint32_t n = sc.c().n_inst;
-    const f3 m = rcp_fixed3(d);
-    const f3 om = o * m;
-    float best = __int_as_float(0x7f800000), best1 = 0.0f;
-    int bi = -1, bt0 = -1, bt1 = -1;
-    bool any = false;
-    for (uint32_t i = 0; i < n; i++) {
-        const float4 a = sc.ia(i);
-        const float4 b = sc.ib(i);
-        const uint32_t kw = __float_as_uint(a.w);
-        const uint32_t kind = kw & 0xffu;
-        float t0, t1 = 0.0f;
-        bool hit;
-        int tr0 = -1, tr1 = -1;
-        if (kind == K_BOX) {
-            // Box::intersect, rt.rs:299-333, slab form: a = pos - half, b = pos + half
-            float ax = fmaf(a.x, m.x, -om.x), bx = fmaf(b.x, m.x, -om.x);
-            float ay = fmaf(a.y, m.y, -om.y), by = fmaf(b.y, m.y, -om.y);
-            float az = fmaf(a.z, m.z, -om.z), bz = fmaf(b.z, m.z, -om.z);
-            t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-            t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-            hit = !(t0 > t1) && !(t1 < 0.0f);
-        } else if (kind == K_SPHERE) {
-            // Sphere::intersect, rt.rs:335-359 with a = d.d = 1 (directions are unit) in half-b form
-            f3 oc = o - xyz(a);
-            float hb = dot(oc, d);
-            float c = fmaf(oc.z, oc.z, fmaf(oc.y, oc.y, fmaf(oc.x, oc.x, -b.x)));
-            float disc = fmaf(hb, hb, -c);
-            float sq = sqrtf(fmaxf(disc, 0.0f));
-            t0 = -hb - sq;
-            t1 = sq - hb;
-            hit = (disc >= 0.0f) && (t0 >= 0.0f);
-        } else if (kind == K_PLANE) {
-            // Plane::intersect, rt.rs:400-412, with the instance transform folded into n_w
-            float num = dot(o, xyz(a)) - b.x;
-            float den = dot(d, xyz(a));
-            t0 = -num * frcp(den);
-            t1 = t0;
-            hit = t0 > 0.0f;
-        } else if (kind == K_BOX_XF) {
-            // rotated box: ray into object space (rt.rs:726-733), then the slab test about the origin
-            const Xf& x = sc.xf(kw >> 8);
-            f3 ol = mulXf(x, o - xyz(a));
-            f3 dl = mulXf(x, d);
-            f3 ml = rcp_fixed3(dl);
-            f3 nl = ol * ml;
-            f3 kl = mk(b.x * fabsf(ml.x), b.y * fabsf(ml.y), b.z * fabsf(ml.z));
-            t0 = fmaxf(fmaxf(-nl.x - kl.x, -nl.y - kl.y), -nl.z - kl.z);
-            t1 = fminf(fminf(kl.x - nl.x, kl.y - nl.y), kl.z - nl.z);
-            hit = !(t0 > t1) && !(t1 < 0.0f);
-        } else {
-            if constexpr ((F & F_MESH) != 0) {
-                f3 ol = o - xyz(a), dl = d;
-                if (b.x != 0.0f) {
-                    const Xf& x = sc.xf(kw >> 8);
-                    ol = mulXf(x, ol);
-                    dl = mulXf(x, d);
-                }
-                hit = mesh_test(sc.c(), __float_as_uint(b.w), ol, dl, &t0, &t1, &tr0, &tr1);
-            } else {
-                hit = false; t0 = 0.0f;
-            }
-        }
-        if constexpr (ANY) {
-            any |= hit;
-        } else {
-            if (hit && t0 < best) {
-                best = t0; bi = (int)i;
-                if constexpr (WANT_T1) best1 = t1;
-                if constexpr ((F & F_MESH) != 0) { bt0 = tr0; bt1 = tr1; }
-            }
+//
+// Instances are grouped by kind, one loop per kind, declaration order inside a kind (a tie
+// between two kinds would need bit-equal results of two different formulas — a rounding
+// coincidence in the reference as well — so only the in-kind order is kept).  Each loop is a
+// Duff's device: the first n % 8 entries run through a fall-through switch whose entries have
+// COMPILE-TIME offsets — with the scene in the kernel-parameter constant bank (ParamView) they
+// need no load, no index arithmetic and no loop control, the constants are FFMA operands — then
+// chunks of 8 with a running base.  The switch runs its entries in descending order, hence its
+// `<=`; the chunks ascend with `<`.
+struct Best {
+    float t0, t1;
+    int bi, tr0, tr1;
+    bool any;
+};
+
+template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
+__device__ __forceinline__ void best_update(Best& B, bool hit, float t0, float t1, int idx, int tr0, int tr1) {
+    if constexpr (ANY) {
+        B.any |= hit;
+    } else {
+        const bool closer = LE ? (t0 <= B.t0) : (t0 < B.t0);
+        if (hit && closer) {
+            B.t0 = t0; B.bi = idx;
+            if constexpr (WANT_T1) B.t1 = t1;
+            if constexpr ((F & F_MESH) != 0) { B.tr0 = tr0; B.tr1 = tr1; }
         }
     }
-    if constexpr (ANY) return any;
-    out->t0 = best; out->t1 = best1; out->inst = bi; out->tri0 = bt0; out->tri1 = bt1;
-    return bi >= 0;
+}
+
+struct RayPre { f3 o, d, m, nom; };  // m = 1/d (Box::intersect's fix-up applied), nom = -o*m
+
+// Box::intersect, rt.rs:299-333, centre/half form: n = (o - pos) m, k = half |m|,
+// t0 = max(-n - k), t1 = min(-n + k); miss iff t0 > t1 or t1 < 0.   9 FFMA + 2 FMNMX3.
+template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
+__device__ __forceinline__ void test_box(Best& B, const RayPre& r, const SlimInst e, int idx) {
+    const float cx = fmaf(e.a.x, r.m.x, r.nom.x), cy = fmaf(e.a.y, r.m.y, r.nom.y), cz = fmaf(e.a.z, r.m.z, r.nom.z);
+    const float ax = fabsf(r.m.x), ay = fabsf(r.m.y), az = fabsf(r.m.z);
+    const float t0 = fmaxf(fmaxf(fmaf(-e.b.x, ax, cx), fmaf(-e.b.y, ay, cy)), fmaf(-e.b.z, az, cz));
+    const float t1 = fminf(fminf(fmaf(e.b.x, ax, cx), fmaf(e.b.y, ay, cy)), fmaf(e.b.z, az, cz));
+    best_update<F, ANY, WANT_T1, LE>(B, fmaxf(t0, 0.0f) <= t1, t0, t1, idx, -1, -1);
+}
+// Sphere::intersect, rt.rs:335-359, with a = d.d = 1 (directions are unit), half-b form
+template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
+__device__ __forceinline__ void test_sphere(Best& B, const RayPre& r, const SlimInst e, int idx) {
+    const f3 oc = r.o - xyz(e.a);
+    const float hb = dot(oc, r.d);
+    const float cc = fmaf(oc.z, oc.z, fmaf(oc.y, oc.y, fmaf(oc.x, oc.x, -e.b.x)));
+    const float disc = fmaf(hb, hb, -cc);
+    const float sq = sqrtf(fmaxf(disc, 0.0f));
+    const float t0 = -hb - sq;
+    best_update<F, ANY, WANT_T1, LE>(B, (disc >= 0.0f) && (t0 >= 0.0f), t0, sq - hb, idx, -1, -1);
+}
+// Plane::intersect, rt.rs:400-412, instance transform folded into n_w
+template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
+__device__ __forceinline__ void test_plane(Best& B, const RayPre& r, const SlimInst e, int idx) {
+    const float t0 = (e.b.x - dot(r.o, xyz(e.a))) * frcp(dot(r.d, xyz(e.a)));
+    best_update<F, ANY, WANT_T1, LE>(B, t0 > 0.0f, t0, t0, idx, -1, -1);
+}
+// rotated box: ray into object space (rt.rs:726-733), slab test about the origin
+template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
+__device__ __forceinline__ void test_bxf(Best& B, const RayPre& r, const SlimInst e, const Xf& x, int idx) {
+    const f3 ol = mulXf(x, r.o - xyz(e.a));
+    const f3 ml = rcp_fixed3(mulXf(x, r.d));
+    const float cx = -ol.x * ml.x, cy = -ol.y * ml.y, cz = -ol.z * ml.z;
+    const float ax = fabsf(ml.x), ay = fabsf(ml.y), az = fabsf(ml.z);
+    const float t0 = fmaxf(fmaxf(fmaf(-e.b.x, ax, cx), fmaf(-e.b.y, ay, cy)), fmaf(-e.b.z, az, cz));
+    const float t1 = fminf(fminf(fmaf(e.b.x, ax, cx), fmaf(e.b.y, ay, cy)), fmaf(e.b.z, az, cz));
+    best_update<F, ANY, WANT_T1, LE>(B, fmaxf(t0, 0.0f) <= t1, t0, t1, idx, -1, -1);
+}
+template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
+__device__ __forceinline__ void test_mesh(Best& B, const SceneCommon& c, const RayPre& r, const SlimInst e, const Xf& x, int idx) {
+    f3 ol = r.o - xyz(e.a), dl = r.d;
+    if (__float_as_uint(e.b.x) != 0u) { ol = mulXf(x, ol); dl = mulXf(x, r.d); }
+    float t0 = 0.0f, t1 = 0.0f;
+    int tr0 = -1, tr1 = -1;
+    const bool hit = mesh_test(c, __float_as_uint(e.b.y), ol, dl, &t0, &t1, &tr0, &tr1);
+    best_update<F, ANY, WANT_T1, LE>(B, hit, t0, t1, idx, tr0, tr1);
+}
+
+// Duff's device over one kind: ENTRY(k, LE) tests entry k of the kind.
+#define MRT_DUFF(n_expr, ENTRY)                                                  \
+    {                                                                            \
+        const uint32_t n__ = (n_expr);                                           \
+        switch (n__ & 7u) {                                                      \
+            case 7: ENTRY(6u, true) [[fallthrough]];                             \
+            case 6: ENTRY(5u, true) [[fallthrough]];                             \
+            case 5: ENTRY(4u, true) [[fallthrough]];                             \
+            case 4: ENTRY(3u, true) [[fallthrough]];                             \
+            case 3: ENTRY(2u, true) [[fallthrough]];                             \
+            case 2: ENTRY(1u, true) [[fallthrough]];                             \
+            case 1: ENTRY(0u, true) [[fallthrough]];                             \
+            default: break;                                                      \
+        }                                                                        \
+        for (uint32_t i__ = n__ & 7u; i__ < n__; i__ += 8u) {                    \
+            _Pragma("unroll") for (uint32_t u__ = 0; u__ < 8u; u__++) { ENTRY(i__ + u__, false) } \
+        }                                                                        \
+    }
+
+template <class V, uint32_t F, bool ANY, bool WANT_T1>
+__device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out) {
+    const SceneCommon& c = sc.c();
+    RayPre r;
+    r.o = o; r.d = d;
+    r.m = rcp_fixed3(d);
+    r.nom = mk(-o.x * r.m.x, -o.y * r.m.y, -o.z * r.m.z);
+    Best B;
+    B.t0 = __int_as_float(0x7f800000); B.t1 = 0.0f; B.bi = -1; B.tr0 = B.tr1 = -1; B.any = false;
+
+#define E_BOX(k, LE) test_box<F, ANY, WANT_T1, LE>(B, r, sc.box(k), (int)(k));
+#define E_SPH(k, LE) test_sphere<F, ANY, WANT_T1, LE>(B, r, sc.sph(k), (int)(c.first[K_SPHERE] + (k)));
+#define E_PLN(k, LE) test_plane<F, ANY, WANT_T1, LE>(B, r, sc.pln(k), (int)(c.first[K_PLANE] + (k)));
+#define E_BXF(k, LE) test_bxf<F, ANY, WANT_T1, LE>(B, r, sc.bxf(k), sc.bxf_m(k), (int)(c.first[K_BOX_XF] + (k)));
+#define E_MSH(k, LE) test_mesh<F, ANY, WANT_T1, LE>(B, c, r, sc.mesh(k), sc.mesh_m(k), (int)(c.first[K_MESH] + (k)));
+    MRT_DUFF(c.cnt[K_BOX], E_BOX)
+    MRT_DUFF(c.cnt[K_SPHERE], E_SPH)
+    MRT_DUFF(c.cnt[K_PLANE], E_PLN)
+    MRT_DUFF(c.cnt[K_BOX_XF], E_BXF)
+    if constexpr ((F & F_MESH) != 0) {
+        for (uint32_t k = 0; k < c.cnt[K_MESH]; k++) { E_MSH(k, false) }
+    }
+#undef E_BOX
+#undef E_SPH
+#undef E_PLN
+#undef E_BXF
+#undef E_MSH
+    if constexpr (ANY) return B.any;
+    out->t0 = B.t0; out->t1 = B.t1; out->inst = B.bi; out->tri0 = B.tr0; out->tri1 = B.tr1;
+    return B.bi >= 0;
 }
 
 // ------------------------------------------------------------------ per-hit data of the winner
 struct Surf {
-    float4 pos_kind, A, B, m0, m1, m2;
-    __device__ __forceinline__ uint32_t kind() const { return __float_as_uint(pos_kind.w) & 0xffu; }
-    __device__ __forceinline__ bool identity() const { return (__float_as_uint(pos_kind.w) >> 8) & 1u; }
+    float4 P, A, m0, m1, m2;
+    __device__ __forceinline__ uint32_t flags() const { return __float_as_uint(P.w); }
+    __device__ __forceinline__ uint32_t kind() const { return flags() & 0xffu; }
+    __device__ __forceinline__ bool identity() const { return (flags() & FAT_IDENT) != 0u; }
+    __device__ __forceinline__ bool textured() const { return (flags() & FAT_TEX) != 0u; }
 };
 __device__ __forceinline__ void load_surf(const FatInst* f, Surf* s) {
-    s->pos_kind = __ldg(&f->pos_kind);
+    s->P = __ldg(&f->P);
     s->A = __ldg(&f->A);
-    s->B = __ldg(&f->B);
-    s->m0 = __ldg(&f->m0);
-    s->m1 = __ldg(&f->m1);
-    s->m2 = __ldg(&f->m2);
+    if ((s->flags() & (FAT_IDENT | FAT_TEX)) != FAT_IDENT) {  // rows only when rotated or textured (ids live in .w)
+        s->m0 = __ldg(&f->m0);
+        s->m1 = __ldg(&f->m1);
+        s->m2 = __ldg(&f->m2);
+    } else {
+        s->m0 = make_float4(1.f, 0.f, 0.f, __uint_as_float(0xffffffffu));
+        s->m1 = make_float4(0.f, 1.f, 0.f, __uint_as_float(0xffffffffu));
+        s->m2 = make_float4(0.f, 0.f, 1.f, __uint_as_float(0xffffffffu));
+    }
 }
 // object-space hit point minus instance pos: rot_y * (look * (hp - pos)), rt.rs:782
 __device__ __forceinline__ f3 to_local(const Surf& s, f3 hp) {
-    f3 r = hp - xyz(s.pos_kind);
+    f3 r = hp - xyz(s.P);
     return s.identity() ? r : mulM(s.m0, s.m1, s.m2, r);
 }
-// Box face of an object-space point: the axis whose |p_i| * (2/size_i) is nearest 1
-// (= largest); Box::normal (rt.rs:414-445) makes the same decision with +-1e-4 windows, and
-// differs only on edges (measure ~1e-4) and when its windows miss (normal = NaN there).
-__device__ __forceinline__ f3 box_face(const Surf& s, f3 pl, f3* p_out) {
-    f3 p = pl * xyz(s.B);
-    *p_out = p;
+// Box::normal, rt.rs:414-445, on p = local point * 2/size: windows |p_i| in 1 +- E, checked
+// x, -x, y, -y, then — the missing `else` at :435 — an independent z test that overrides.
+// (The reference's windows are half-open, [1-E, 1+E); the open form used here differs only when
+// |p_i| equals a window end exactly.)  When no window matches the reference normalises a zero
+// vector (NaN normal, measured 1e-7 of hits); the nearest face is taken instead.
+__device__ __forceinline__ f3 box_face(f3 p) {
     const float ax = fabsf(p.x), ay = fabsf(p.y), az = fabsf(p.z);
-    // Box::normal's windows [1-E, 1+E) / [-1-E, -1+E) and its if-chain, rt.rs:418-441: x before y,
-    // then — missing `else` at :435 — an independent z test that overrides.
-    const float lo = 1.0f - MRT_E, hi = 1.0f + MRT_E;
-    const bool wx = p.x >= 0.0f ? (ax >= lo && ax < hi) : (ax > lo && ax <= hi);
-    const bool wy = p.y >= 0.0f ? (ay >= lo && ay < hi) : (ay > lo && ay <= hi);
-    const bool wz = p.z >= 0.0f ? (az >= lo && az < hi) : (az > lo && az <= hi);
-    if (wz) return mk(0.f, 0.f, copysignf(1.0f, p.z));
-    if (wx) return mk(copysignf(1.0f, p.x), 0.f, 0.f);
-    if (wy) return mk(0.f, copysignf(1.0f, p.y), 0.f);
-    // no window matched: the reference normalises a zero vector (NaN normal, ~1e-7 of hits);
-    // take the nearest face instead of poisoning the path.
-    if (az >= ax && az >= ay) return mk(0.f, 0.f, copysignf(1.0f, p.z));
-    if (ax >= ay) return mk(copysignf(1.0f, p.x), 0.f, 0.f);
-    return mk(0.f, copysignf(1.0f, p.y), 0.f);
+    const bool wx = fabsf(ax - 1.0f) < MRT_E, wy = fabsf(ay - 1.0f) < MRT_E, wz = fabsf(az - 1.0f) < MRT_E;
+    bool fz = wz, fx = !wz && wx, fy = !wz && !wx && wy;
+    if (!(fz || fx || fy)) {
+        fz = az >= ax && az >= ay;
+        fx = !fz && ax >= ay;
+        fy = !fz && !fx;
+    }
+    return mk(fx ? copysignf(1.0f, p.x) : 0.0f, fy ? copysignf(1.0f, p.y) : 0.0f, fz ? copysignf(1.0f, p.z) : 0.0f);
 }
 // Renderer::normal, rt.rs:776-793: kind normal of the object-space hit point, pushed through
-// the FORWARD transform again (rt.rs:792) and normalised.
-__device__ __forceinline__ f3 surf_normal(const SceneCommon& c, const Surf& s, f3 pl, int tri, uint32_t mesh_first_tri) {
+// the FORWARD transform again (rt.rs:792) and normalised.  Unit inputs through an orthonormal M
+// stay unit to 1e-7, so only mesh normals need the rsqrt.
+__device__ __forceinline__ f3 surf_normal(const SceneCommon& c, const Surf& s, f3 pl, int tri) {
     const uint32_t k = s.kind();
-    f3 n;
     if (k == K_PLANE) return xyz(s.A);  // precomputed norm(M n)
-    if (k == K_SPHERE) n = pl;
+    f3 n;
+    if (k == K_SPHERE) n = pl * s.A.x;  // (hit - pos) / r
     else if (k == K_MESH) {
-        const DTri* tp = &c.tri[mesh_first_tri + (uint32_t)tri];
+        const DTri* tp = &c.tri[__float_as_uint(s.A.x) + (uint32_t)tri];
         n = cross(xyz(__ldg(&tp->e0)), xyz(__ldg(&tp->e1)));  // rt.rs:459-466
-    } else {
-        f3 p;
-        n = box_face(s, pl, &p);
-    }
+    } else n = box_face(pl * xyz(s.A));
     if (!s.identity()) n = mulM(s.m0, s.m1, s.m2, n);
-    return normalize(n);
+    if (k == K_MESH) n = normalize(n);
+    return n;
 }
 
 // UV impls, rt.rs:468-548, on the object-space point (pl = point - pos; plane uses the absolute
@@ -375,13 +455,13 @@ __device__ __forceinline__ float2 surf_uv(const Surf& s, f3 pl) {
         return make_float2(0.5f + 0.5f * atan2f(v.x, -v.y) * 0.31830988618379067154f, 0.5f - 0.5f * v.z);
     }
     if (k == K_PLANE) {
-        f3 h = pl + xyz(s.pos_kind);
+        f3 h = pl + xyz(s.P);
         float x = h.x + 0.5f; x = x - truncf(x); if (x < 0.0f) x = 1.0f + x;
         float y = h.y + 0.5f; y = y - truncf(y); if (y < 0.0f) y = 1.0f + y;
         return make_float2(x, y);
     }
     if (k == K_BOX || k == K_BOX_XF) {
-        f3 p = pl * xyz(s.B);
+        f3 p = pl * xyz(s.A);
         const float pl_ = 1.0f - MRT_E, ph = 1.0f + MRT_E, nl = -1.0f - MRT_E, nh = -1.0f + MRT_E;
         const float th = 1.0f / 3.0f;
         // same chain and priorities as rt.rs:475-514 (x and y faces return before z is looked at)
@@ -420,13 +500,13 @@ struct Mat {
 // material getters, rt.rs:811-863, all maps fetched at the same uv
 template <uint32_t F>
 __device__ __forceinline__ void load_mat(const SceneCommon& c, const FatInst* f, const Surf& s, f3 pl, Mat* m) {
-    const float4 ae = __ldg(&f->albedo_emit);
-    const float4 r = __ldg(&f->rmgo);
+    const float4 ae = __ldg(&f->C);
+    const float4 r = __ldg(&f->R);
     m->color = xyz(ae); m->emit = ae.w;
     m->rough = r.x; m->metal = r.y; m->glass = r.z; m->opacity = r.w; m->metal_raw = r.y;
     if constexpr ((F & F_TEX) != 0) {
-        const uint32_t t0 = __float_as_uint(s.m0.w), t1 = __float_as_uint(s.m1.w), t2 = __float_as_uint(s.m2.w);
-        if ((t0 & t1 & t2) != 0xffffffffu) {
+        if (s.textured()) {
+            const uint32_t t0 = __float_as_uint(s.m0.w), t1 = __float_as_uint(s.m1.w), t2 = __float_as_uint(s.m2.w);
             const float2 uv = surf_uv(s, pl);
             if ((t0 & 0xffffu) != 0xffffu) m->color = m->color * xyz(tex_fetch(c, t0 & 0xffffu, uv));
             if ((t0 >> 16) != 0xffffu) m->rough = tex_fetch(c, t0 >> 16, uv).x;

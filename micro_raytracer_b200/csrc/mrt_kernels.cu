@@ -77,10 +77,9 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
         const FatInst* fat = c.fat + h.inst;
         Surf s;
         load_surf(fat, &s);
-        const uint32_t mesh_ft = __float_as_uint(s.A.x);
         f3 hp = fma3(d, h.t0, o);
         f3 pl = to_local(s, hp);
-        f3 n = surf_normal(c, s, pl, h.tri0, mesh_ft);
+        f3 n = surf_normal(c, s, pl, h.tri0);
         Mat m;
         load_mat<F>(c, fat, s, pl, &m);
 
@@ -103,7 +102,7 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
             float rough = m.rough;
             if (m.metal_raw == 0.0f && m.opacity != 0.0f && u.x < 0.80f) rough = 1.0f;
             const f3 nn = rand_normal(n, rough, u.y, u.z);
-            nd = normalize(reflect3(d, nn));
+            nd = reflect3(d, nn);  // unit d about unit nn stays unit (the reference's .norm() is a no-op to 1e-7)
             no = fma3(nd, MRT_E, hp);
         }
         // 15 % chance to keep reflecting for transparent material, rt.rs:1051-1059
@@ -115,7 +114,7 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
                     // exit hit: point, normal and material at t1 (rt.rs:886-894)
                     const f3 hp1 = fma3(d, h.t1, o);
                     const f3 pl1 = to_local(s, hp1);
-                    const f3 n1 = surf_normal(c, s, pl1, h.tri1, mesh_ft);
+                    const f3 n1 = surf_normal(c, s, pl1, h.tri1);
                     Mat m1;
                     load_mat<F>(c, fat, s, pl1, &m1);
                     // Ray::refract, rt.rs:574-589 ; Vec3f::refract, lin.rs:96-105
@@ -206,11 +205,10 @@ __global__ void __launch_bounds__(128) primary_kernel(const __grid_constant__ Gl
         const FatInst* fat = c.fat + h.inst;
         Surf s;
         load_surf(fat, &s);
-        const uint32_t mesh_ft = __float_as_uint(s.A.x);
         const f3 p0 = to_local(s, fma3(d, h.t0, o));
         const f3 p1 = to_local(s, fma3(d, h.t1, o));
-        const f3 n0 = surf_normal(c, s, p0, h.tri0, mesh_ft);
-        const f3 n1 = surf_normal(c, s, p1, h.tri1, mesh_ft);
+        const f3 n0 = normalize(surf_normal(c, s, p0, h.tri0));
+        const f3 n1 = normalize(surf_normal(c, s, p1, h.tri1));
         r.t0 = h.t0; r.t1 = h.t1;
         const uint32_t oi = obj_inst[h.inst];
         r.obj = (int)(oi & 0xffffu); r.inst = (int)(oi >> 16);
