@@ -157,6 +157,7 @@ FilmParams make_film_params(const mrt_ctx* c) {
     fp.aprt = f.aprt; fp.foc = f.foc;
     const HM m = transform_of(f.cam_dir);
     for (int i = 0; i < 9; i++) fp.cam_M[i] = m.m[i];
+    fp.cam_identity = is_identity(m) ? 1u : 0u;
     fp.fw = (float)f.res[0] * f.ssaa;
     fp.fh = (float)f.res[1] * f.ssaa;
     const float tan_fov = std::tan((0.5f * f.fov) * (3.14159265358979323846f / 180.0f));  // rt.rs:902
@@ -381,8 +382,13 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
             } else if (o.kind == MRT_BOX) {
                 kind = ident ? K_BOX : K_BOX_XF;
                 si.a = make_float4(pos.x, pos.y, pos.z, 0.0f);
-                si.b = make_float4(0.5f * o.param[0], 0.5f * o.param[1], 0.5f * o.param[2], 0.0f);
-                if (!ident) bxf_m.push_back(x);
+                if (ident) {
+                    si.a.w = 0.5f * o.param[0];
+                    si.b = make_float4(0.5f * o.param[1], 0.5f * o.param[2], 0.0f, 0.0f);
+                } else {
+                    si.b = make_float4(0.5f * o.param[0], 0.5f * o.param[1], 0.5f * o.param[2], 0.0f);
+                    bxf_m.push_back(x);
+                }
                 fi.A = make_float4((1.0f / o.param[0]) * 2.0f, (1.0f / o.param[1]) * 2.0f, (1.0f / o.param[2]) * 2.0f, 0.0f);  // rt.rs:416
             } else {
                 kind = K_MESH;

@@ -30,7 +30,7 @@ enum : uint32_t {
 // The closest-hit loops walk one table per primitive kind (no per-instance dispatch), each in
 // declaration order; the FatInst table is sorted the same way (kind, then declaration order).
 struct SlimInst {
-    // box    : a.xyz = centre            b.xyz = half sizes        (identity transform)
+    // box    : a = (centre.xyz, half.x)  b.xy = half.yz            (identity transform; 6 floats = 2 uniform loads)
     // sphere : a.xyz = centre            b.x = r^2
     // plane  : a.xyz = n_w = M^T n^     b.x = pos . n_w          (t = -(o.n_w - b.x)/(d.n_w))
     // box_xf : a.xyz = pos               b.xyz = half              (+ its Xf at the same index)
@@ -113,6 +113,7 @@ struct FilmParams {
     float cam_M[9];       // rot_y(cam.dir) * lookat(cam.dir, up)   (rt.rs:925-930)
     float fw, fh;         // res * ssaa as f32 (rt.rs:938-939)
     float fy;             // 1 / (2 tan(fov/2))  (rt.rs:902-906)
+    uint32_t cam_identity;  // cam_M == I: skip the rotation
 };
 
 // ------------------------------------------------------------------ small vector helpers
@@ -138,7 +139,11 @@ __device__ __forceinline__ f3 mulXf(const Xf& x, f3 v) {
             fmaf(x.m[6], v.z, fmaf(x.m[5], v.y, x.m[4] * v.x)),
             fmaf(x.m[10], v.z, fmaf(x.m[9], v.y, x.m[8] * v.x))};
 }
-__device__ __forceinline__ float frcp(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ float frcp(float x) {  // one MUFU.RCP
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 // Box::intersect's reciprocal with the zero-division workaround, rt.rs:303-316
 __device__ __forceinline__ float rcp_fixed(float d) {
@@ -272,6 +277,40 @@ struct Best {
     bool any;
 };
 
+// hit  <=>  t0 <= t1 and t1 >= 0 (Box) — folded with "closer than the best so far" into
+// t0 < min(t1, best) and t1 >= 0: FMNMX + FSETP + FSETP.AND + 2 selects.  (t0 == t1, a ray grazing
+// an edge exactly, counts as a miss here; measure zero.)
+template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
+__device__ __forceinline__ void best_update_slab(Best& B, float t0, float t1, int idx) {
+    if constexpr (ANY) {
+        B.any |= (t0 <= t1) && (t1 >= 0.0f);
+    } else if constexpr (WANT_T1 || (F & F_MESH) != 0) {
+        const bool closer = LE ? (t0 <= B.t0) : (t0 < B.t0);
+        if (fmaxf(t0, 0.0f) <= t1 && closer) {
+            B.t0 = t0; B.bi = idx;
+            if constexpr (WANT_T1) B.t1 = t1;
+            if constexpr ((F & F_MESH) != 0) { B.tr0 = -1; B.tr1 = -1; }
+        }
+    } else {
+        if constexpr (LE)
+            asm("{\n\t.reg .pred p, q;\n\t.reg .f32 tm;\n\t"
+                "min.ftz.f32 tm, %3, %0;\n\t"
+                "setp.ge.ftz.f32 p, %3, 0f00000000;\n\t"
+                "setp.le.and.ftz.f32 q, %2, tm, p;\n\t"
+                "selp.f32 %0, %2, %0, q;\n\t"
+                "selp.b32 %1, %4, %1, q;\n\t}"
+                : "+f"(B.t0), "+r"(B.bi) : "f"(t0), "f"(t1), "r"(idx));
+        else
+            asm("{\n\t.reg .pred p, q;\n\t.reg .f32 tm;\n\t"
+                "min.ftz.f32 tm, %3, %0;\n\t"
+                "setp.ge.ftz.f32 p, %3, 0f00000000;\n\t"
+                "setp.lt.and.ftz.f32 q, %2, tm, p;\n\t"
+                "selp.f32 %0, %2, %0, q;\n\t"
+                "selp.b32 %1, %4, %1, q;\n\t}"
+                : "+f"(B.t0), "+r"(B.bi) : "f"(t0), "f"(t1), "r"(idx));
+    }
+}
+
 template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
 __device__ __forceinline__ void best_update(Best& B, bool hit, float t0, float t1, int idx, int tr0, int tr1) {
     if constexpr (ANY) {
@@ -294,9 +333,9 @@ template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
 __device__ __forceinline__ void test_box(Best& B, const RayPre& r, const SlimInst e, int idx) {
     const float cx = fmaf(e.a.x, r.m.x, r.nom.x), cy = fmaf(e.a.y, r.m.y, r.nom.y), cz = fmaf(e.a.z, r.m.z, r.nom.z);
     const float ax = fabsf(r.m.x), ay = fabsf(r.m.y), az = fabsf(r.m.z);
-    const float t0 = fmaxf(fmaxf(fmaf(-e.b.x, ax, cx), fmaf(-e.b.y, ay, cy)), fmaf(-e.b.z, az, cz));
-    const float t1 = fminf(fminf(fmaf(e.b.x, ax, cx), fmaf(e.b.y, ay, cy)), fmaf(e.b.z, az, cz));
-    best_update<F, ANY, WANT_T1, LE>(B, fmaxf(t0, 0.0f) <= t1, t0, t1, idx, -1, -1);
+    const float t0 = fmaxf(fmaxf(fmaf(-e.a.w, ax, cx), fmaf(-e.b.x, ay, cy)), fmaf(-e.b.y, az, cz));
+    const float t1 = fminf(fminf(fmaf(e.a.w, ax, cx), fmaf(e.b.x, ay, cy)), fmaf(e.b.y, az, cz));
+    best_update_slab<F, ANY, WANT_T1, LE>(B, t0, t1, idx);
 }
 // Sphere::intersect, rt.rs:335-359, with a = d.d = 1 (directions are unit), half-b form
 template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
@@ -324,7 +363,7 @@ __device__ __forceinline__ void test_bxf(Best& B, const RayPre& r, const SlimIns
     const float ax = fabsf(ml.x), ay = fabsf(ml.y), az = fabsf(ml.z);
     const float t0 = fmaxf(fmaxf(fmaf(-e.b.x, ax, cx), fmaf(-e.b.y, ay, cy)), fmaf(-e.b.z, az, cz));
     const float t1 = fminf(fminf(fmaf(e.b.x, ax, cx), fmaf(e.b.y, ay, cy)), fmaf(e.b.z, az, cz));
-    best_update<F, ANY, WANT_T1, LE>(B, fmaxf(t0, 0.0f) <= t1, t0, t1, idx, -1, -1);
+    best_update_slab<F, ANY, WANT_T1, LE>(B, t0, t1, idx);
 }
 template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
 __device__ __forceinline__ void test_mesh(Best& B, const SceneCommon& c, const RayPre& r, const SlimInst e, const Xf& x, int idx) {
@@ -373,7 +412,7 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
     MRT_DUFF(c.cnt[K_BOX], E_BOX)
     MRT_DUFF(c.cnt[K_SPHERE], E_SPH)
     MRT_DUFF(c.cnt[K_PLANE], E_PLN)
-    MRT_DUFF(c.cnt[K_BOX_XF], E_BXF)
+    for (uint32_t k = 0; k < c.cnt[K_BOX_XF]; k++) { E_BXF(k, false) }
     if constexpr ((F & F_MESH) != 0) {
         for (uint32_t k = 0; k < c.cnt[K_MESH]; k++) { E_MSH(k, false) }
     }
@@ -419,14 +458,15 @@ __device__ __forceinline__ f3 to_local(const Surf& s, f3 hp) {
 // |p_i| equals a window end exactly.)  When no window matches the reference normalises a zero
 // vector (NaN normal, measured 1e-7 of hits); the nearest face is taken instead.
 __device__ __forceinline__ f3 box_face(f3 p) {
-    const float ax = fabsf(p.x), ay = fabsf(p.y), az = fabsf(p.z);
-    const bool wx = fabsf(ax - 1.0f) < MRT_E, wy = fabsf(ay - 1.0f) < MRT_E, wz = fabsf(az - 1.0f) < MRT_E;
-    bool fz = wz, fx = !wz && wx, fy = !wz && !wx && wy;
-    if (!(fz || fx || fy)) {
-        fz = az >= ax && az >= ay;
-        fx = !fz && ax >= ay;
-        fy = !fz && !fx;
-    }
+    // distance of |p_i| from 1; a windowed axis gets a negative score that encodes the
+    // reference's priority (z over x over y), otherwise the nearest face wins.  Branch-free.
+    const float ex = fabsf(fabsf(p.x) - 1.0f), ey = fabsf(fabsf(p.y) - 1.0f), ez = fabsf(fabsf(p.z) - 1.0f);
+    const float sz = ez < MRT_E ? -3.0f : ez;
+    const float sx = ex < MRT_E ? -2.0f : ex;
+    const float sy = ey < MRT_E ? -1.0f : ey;
+    const bool fz = sz <= sx && sz <= sy;
+    const bool fx = !fz && sx <= sy;
+    const bool fy = !fz && !fx;
     return mk(fx ? copysignf(1.0f, p.x) : 0.0f, fy ? copysignf(1.0f, p.y) : 0.0f, fz ? copysignf(1.0f, p.z) : 0.0f);
 }
 // Renderer::normal, rt.rs:776-793: kind normal of the object-space hit point, pushed through

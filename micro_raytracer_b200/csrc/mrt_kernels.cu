@@ -30,7 +30,7 @@ __device__ __forceinline__ f3 pixel_focus_vec(const FilmParams& fp, uint32_t px,
 __device__ __forceinline__ void camera_ray(const FilmParams& fp, f3 q, float u1, float u2, f3* o, f3* d) {
     const float jx = (u1 - 0.5f) * fp.aprt, jz = (u2 - 0.5f) * fp.aprt;
     const f3 nd = normalize(mk(q.x - jx, q.y, q.z - jz));
-    const f3 dd = mk(fmaf(fp.cam_M[2], nd.z, fmaf(fp.cam_M[1], nd.y, fp.cam_M[0] * nd.x)),
+    const f3 dd = fp.cam_identity ? nd : mk(fmaf(fp.cam_M[2], nd.z, fmaf(fp.cam_M[1], nd.y, fp.cam_M[0] * nd.x)),
                      fmaf(fp.cam_M[5], nd.z, fmaf(fp.cam_M[4], nd.y, fp.cam_M[3] * nd.x)),
                      fmaf(fp.cam_M[8], nd.z, fmaf(fp.cam_M[7], nd.y, fp.cam_M[6] * nd.x)));
     const f3 pos = mk(fp.cam_pos[0] + jx, fp.cam_pos[1], fp.cam_pos[2] + jz);

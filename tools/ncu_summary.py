@@ -1,0 +1,30 @@
+"""Summarise an .ncu-rep (raw + source pages) into a short text file for profiles/."""
+import csv, subprocess, sys, io
+rep = sys.argv[1]
+paths = float(sys.argv[2]) if len(sys.argv) > 2 else None
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units, vals = rows[0], rows[1], rows[2]
+want = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "smsp__thread_inst_executed.sum",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum",
+        "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum", "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum",
+        "sm__sass_thread_inst_executed_op_fp32_pred_on.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
+        "smsp__sass_average_branch_targets_threads_uniform.pct", "sm__inst_executed_pipe_fp16.avg.pct_of_peak_sustained_active"]
+print(f"# ncu summary of {rep}")
+for w in want:
+    if w in hdr:
+        i = hdr.index(w)
+        print(f"{w} [{units[i]}] = {vals[i]}")
+for i, h in enumerate(hdr):
+    if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio"):
+        print(f"{h} = {vals[i]}")
+if paths:
+    i = hdr.index("smsp__inst_executed.sum"); j = hdr.index("smsp__thread_inst_executed.sum")
+    print(f"warp-instructions per path x32 = {float(vals[i]) * 32 / paths:.1f}; active thread-instructions per path = {float(vals[j]) / paths:.1f}")
