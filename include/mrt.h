@@ -151,6 +151,16 @@ int mrt_set_frame(mrt_ctx* ctx, const mrt_frame* frame);
  * in for rand::thread_rng (unseedable in the reference). */
 int mrt_set_rt(mrt_ctx* ctx, uint32_t bounce, float loss, uint64_t seed);
 
+/* Behaviour switches.  An option takes effect at the next mrt_set_scene.
+ *   MRT_OPT_NORMAL_SPACE   how Renderer::normal (rt.rs:776-793) returns the kind normal n of a
+ *                          ROTATED instance (identity instances are unaffected):
+ *     MRT_NORMAL_FORWARD_XF  norm(rot_y * (look * n)) — rt.rs:792 as written at HEAD (default)
+ *     MRT_NORMAL_OBJECT      norm(n) — what the revision that rendered doc/out3.png (README's
+ *                            CornellBox2 image) did; kept so that golden image stays reproducible. */
+typedef enum mrt_option { MRT_OPT_NORMAL_SPACE = 1 } mrt_option;
+enum { MRT_NORMAL_FORWARD_XF = 0, MRT_NORMAL_OBJECT = 1 };
+int mrt_set_option(mrt_ctx* ctx, uint32_t option, uint32_t value);
+
 /* Multi-GPU sample split: this context renders global sample indices
  * rank, rank + world, rank + 2*world, ...  Default rank 0 of world 1. */
 int mrt_set_partition(mrt_ctx* ctx, uint32_t rank, uint32_t world);

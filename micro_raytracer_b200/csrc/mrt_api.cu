@@ -115,6 +115,7 @@ struct mrt_ctx {
     uint32_t passes = 0;        // passes this context rendered (local)
     uint32_t passes_total = 0;  // passes the accumulator holds (after an external reduce)
     uint32_t spp_per_launch = 128;
+    uint32_t normal_space = MRT_NORMAL_FORWARD_XF;  // MRT_OPT_NORMAL_SPACE
 
     // film
     DevBuf<float4> d_accum;
@@ -377,7 +378,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
                                M.m[2] * nh.x + M.m[5] * nh.y + M.m[8] * nh.z};
                 si.a = make_float4(nw.x, nw.y, nw.z, 0.0f);
                 si.b = make_float4(hdot(pos, nw), 0.0f, 0.0f, 0.0f);
-                const H3 ns = hnorm(hmul(M, nraw));  // Renderer::normal, rt.rs:786,792
+                const H3 ns = c->normal_space == MRT_NORMAL_OBJECT ? hnorm(nraw) : hnorm(hmul(M, nraw));  // Renderer::normal, rt.rs:786,792
                 fi.A = make_float4(ns.x, ns.y, ns.z, 0.0f);
             } else if (o.kind == MRT_BOX) {
                 kind = ident ? K_BOX : K_BOX_XF;
@@ -397,7 +398,8 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
                 mesh_m.push_back(x);
                 fi.A = make_float4(u2f(meshes[o.mesh].first_tri), 0.0f, 0.0f, 0.0f);
             }
-            fi.P = make_float4(pos.x, pos.y, pos.z, u2f(kind | (ident ? FAT_IDENT : 0u) | (textured ? FAT_TEX : 0u)));
+            fi.P = make_float4(pos.x, pos.y, pos.z, u2f(kind | (ident ? FAT_IDENT : 0u) | (textured ? FAT_TEX : 0u) |
+                                                        ((!ident && c->normal_space == MRT_NORMAL_FORWARD_XF) ? FAT_NXF : 0u)));
             fi.m0 = make_float4(M.m[0], M.m[1], M.m[2], u2f(pack_ids(mt.tex, mt.rmap)));
             fi.m1 = make_float4(M.m[3], M.m[4], M.m[5], u2f(pack_ids(mt.mmap, mt.gmap)));
             fi.m2 = make_float4(M.m[6], M.m[7], M.m[8], u2f(pack_ids(mt.omap, mt.emap)));
@@ -491,6 +493,13 @@ int mrt_set_rt(mrt_ctx* c, uint32_t bounce, float loss, uint64_t seed) {
     if (!c) return MRT_ERR_INVALID;
     if (bounce > 0x3fffffffu) return fail(c, MRT_ERR_INVALID, "bounce too large");
     c->bounce = bounce; c->loss = loss; c->seed = seed;
+    return MRT_OK;
+}
+
+int mrt_set_option(mrt_ctx* c, uint32_t option, uint32_t value) {
+    if (!c) return MRT_ERR_INVALID;
+    if (option != MRT_OPT_NORMAL_SPACE || value > MRT_NORMAL_OBJECT) return fail(c, MRT_ERR_INVALID, "unknown option or value");
+    c->normal_space = value;  // read by the next mrt_set_scene
     return MRT_OK;
 }
 

@@ -39,7 +39,7 @@ struct SlimInst {
 };
 struct Xf { float m[12]; };  // rows of M = rot_y * look (rt.rs:726-727), padded to 3 x float4
 
-enum : uint32_t { FAT_IDENT = 0x100u, FAT_TEX = 0x200u };
+enum : uint32_t { FAT_IDENT = 0x100u, FAT_TEX = 0x200u, FAT_NXF = 0x400u /* kind normal goes through M again, rt.rs:792 */ };
 struct FatInst {
     float4 P;          // pos.xyz, w = kind | FAT_IDENT | FAT_TEX (bits)
     float4 A;          // box: 2/size   sphere: (1/r, r, 0)   plane: shading normal norm(M n)   mesh: x = first_tri (bits)
@@ -433,6 +433,7 @@ struct Surf {
     __device__ __forceinline__ uint32_t kind() const { return flags() & 0xffu; }
     __device__ __forceinline__ bool identity() const { return (flags() & FAT_IDENT) != 0u; }
     __device__ __forceinline__ bool textured() const { return (flags() & FAT_TEX) != 0u; }
+    __device__ __forceinline__ bool normal_xf() const { return (flags() & FAT_NXF) != 0u; }
 };
 __device__ __forceinline__ void load_surf(const FatInst* f, Surf* s) {
     s->P = __ldg(&f->P);
@@ -470,7 +471,7 @@ __device__ __forceinline__ f3 box_face(f3 p) {
     return mk(fx ? copysignf(1.0f, p.x) : 0.0f, fy ? copysignf(1.0f, p.y) : 0.0f, fz ? copysignf(1.0f, p.z) : 0.0f);
 }
 // Renderer::normal, rt.rs:776-793: kind normal of the object-space hit point, pushed through
-// the FORWARD transform again (rt.rs:792) and normalised.  Unit inputs through an orthonormal M
+// the FORWARD transform again (rt.rs:792; unless MRT_NORMAL_OBJECT is selected) and normalised.  Unit inputs through an orthonormal M
 // stay unit to 1e-7, so only mesh normals need the rsqrt.
 __device__ __forceinline__ f3 surf_normal(const SceneCommon& c, const Surf& s, f3 pl, int tri) {
     const uint32_t k = s.kind();
@@ -481,7 +482,7 @@ __device__ __forceinline__ f3 surf_normal(const SceneCommon& c, const Surf& s, f
         const DTri* tp = &c.tri[__float_as_uint(s.A.x) + (uint32_t)tri];
         n = cross(xyz(__ldg(&tp->e0)), xyz(__ldg(&tp->e1)));  // rt.rs:459-466
     } else n = box_face(pl * xyz(s.A));
-    if (!s.identity()) n = mulM(s.m0, s.m1, s.m2, n);
+    if (s.normal_xf()) n = mulM(s.m0, s.m1, s.m2, n);  // MRT_OPT_NORMAL_SPACE
     if (k == K_MESH) n = normalize(n);
     return n;
 }

@@ -20,6 +20,7 @@ from . import abi
 from .scene import Frame, PackedScene, RayTracer, Scene, pack_scene
 
 _LIB_NAME = "libmrt.so"
+OPT_NORMAL_SPACE, NORMAL_FORWARD_XF, NORMAL_OBJECT = 1, 0, 1  # include/mrt.h
 _lib = None
 
 
@@ -47,6 +48,7 @@ def declare(lib, prefix: str = "mrt_"):
     fn("set_frame", P, C.POINTER(abi.MrtFrame))
     fn("set_rt", P, u32, f32, u64)
     fn("set_partition", P, u32, u32)
+    fn("set_option", P, u32, u32)
     fn("execute", P, u32, C.POINTER(C.c_double))
     fn("reset", P)
     fn("film_size", P, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32))
@@ -140,6 +142,11 @@ class Sampler:
 
     def set_rt(self, rt: RayTracer):
         self._check(self._f("set_rt")(self._ctx, int(rt.bounce), float(rt.loss), int(self.seed)))
+
+    def set_option(self, option: int, value: int):
+        """mrt_set_option; the scene is re-sent on the next execute so the option takes effect."""
+        self._check(self._f("set_option")(self._ctx, int(option), int(value)))
+        self._scene_key = None
 
     def set_partition(self, rank: int, world: int):
         self._check(self._f("set_partition")(self._ctx, int(rank), int(world)))

@@ -185,6 +185,7 @@ struct Scene {
     std::vector<Mesh> meshes;
     V3 sky_color{0, 0, 0};
     float sky_pwr = 0.5f;
+    uint32_t normal_space = MRT_NORMAL_FORWARD_XF;  // MRT_OPT_NORMAL_SPACE, see include/mrt.h
 };
 struct Hit {  // rt.rs:54-61
     int obj = -1, inst = -1, idx = -1;
@@ -447,6 +448,10 @@ V3 obj_normal(const Scene& sc, const Object& o, const Instance& inst, const Hit&
         case MRT_TRIANGLE: n = tri_normal(o.tri); break;
         default: n = tri_normal(sc.meshes[o.mesh].tris[hit.idx]); break;
     }
+    // rt.rs:792 at HEAD pushes n through the FORWARD transform again.  doc/out3.png (the README's
+    // CornellBox2 render) was produced by a revision that returned the object-space normal: with
+    // this switch the oracle reproduces that image (tests/test_oracle_golden.py).
+    if (sc.normal_space == MRT_NORMAL_OBJECT) return norm(n);
     return norm(rot_y * (look * n));
 }
 
@@ -638,19 +643,21 @@ V3 direct_light(const Scene& sc, const PathItem& it) {
 V3 reduce_light_literal(const Scene& sc, const RtParams& rt, const Frame& f, float cx, float cy,
                         const PathRng& rng, Stats* st) {
     st->paths++;
-    {   // it.clone().count() == 0  (rt.rs:957): a full throw-away trace with its own randoms
+    // RayTracer::iter casts the camera ray ONCE (rt.rs:948); it.clone() copies it, so the
+    // throw-away count trace and the collected trace start from the same primary ray.
+    Block c = rng.cam();
+    const Ray ray0 = rt_iter(cx, cy, f, c.u[0], c.u[1]);
+    {   // it.clone().count() == 0  (rt.rs:957): a full throw-away trace with its own bounce randoms
         PathRng rng0 = rng;
         rng0.key ^= 0xA5A5A5A5u;
-        Block c = rng0.cam();
-        Ray ray = rt_iter(cx, cy, f, c.u[0], c.u[1]);
+        Ray ray = ray0;
         PathItem item;
         Stats dummy;
         size_t count = 0;
         while (iter_next(sc, rt, &ray, rng0, &item, &dummy)) count++;
         if (count == 0) { st->hist[0]++; return sc.sky_color; }
     }
-    Block c = rng.cam();
-    Ray ray = rt_iter(cx, cy, f, c.u[0], c.u[1]);
+    Ray ray = ray0;
     std::vector<PathItem> path;
     PathItem item;
     while (iter_next(sc, rt, &ray, rng, &item, st)) path.push_back(item);
@@ -790,6 +797,7 @@ struct mrt_cpu_ctx {
     uint64_t seed = 0x5EED;
     uint32_t rank = 0, world = 1;
     int mode = MRT_CPU_FORWARD;
+    uint32_t normal_space = MRT_NORMAL_FORWARD_XF;
     uint32_t nw = 0, nh = 0, passes = 0;
     std::vector<float> colors;  // nw*nh*3, f32 `+=` per pass like Sampler.colors (sampler.rs:60-70)
     Stats stats;
@@ -881,6 +889,7 @@ int mrt_cpu_set_scene(mrt_cpu_ctx* c, const mrt_scene* s) {
         const mrt_light& l = s->lights[i];
         sc.lights.push_back({l.kind, {l.v[0], l.v[1], l.v[2]}, l.pwr, {l.color[0], l.color[1], l.color[2]}});
     }
+    sc.normal_space = c->normal_space;
     c->scene = std::move(sc);
     for (uint32_t i = 0; i < s->n_textures; i++)
         c->scene.tex[i].dat = c->scene.texels.data() + 3 * s->textures[i].first_texel;
@@ -916,6 +925,13 @@ int mrt_cpu_set_partition(mrt_cpu_ctx* c, uint32_t rank, uint32_t world) {
 int mrt_cpu_set_mode(mrt_cpu_ctx* c, int mode) {
     if (!c || (mode != MRT_CPU_LITERAL && mode != MRT_CPU_FORWARD)) return MRT_ERR_INVALID;
     c->mode = mode;
+    return MRT_OK;
+}
+int mrt_cpu_set_option(mrt_cpu_ctx* c, uint32_t option, uint32_t value) {
+    if (!c) return MRT_ERR_INVALID;
+    if (option != MRT_OPT_NORMAL_SPACE || value > MRT_NORMAL_OBJECT) return fail(c, MRT_ERR_INVALID, "unknown option or value");
+    c->normal_space = value;
+    c->scene.normal_space = value;
     return MRT_OK;
 }
 int mrt_cpu_reset(mrt_cpu_ctx* c) {

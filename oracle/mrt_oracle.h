@@ -48,6 +48,7 @@ int mrt_cpu_set_frame(mrt_cpu_ctx* ctx, const mrt_frame* frame);
 int mrt_cpu_set_rt(mrt_cpu_ctx* ctx, uint32_t bounce, float loss, uint64_t seed);
 int mrt_cpu_set_partition(mrt_cpu_ctx* ctx, uint32_t rank, uint32_t world);
 int mrt_cpu_set_mode(mrt_cpu_ctx* ctx, int mode);
+int mrt_cpu_set_option(mrt_cpu_ctx* ctx, uint32_t option, uint32_t value);
 
 int mrt_cpu_execute(mrt_cpu_ctx* ctx, uint32_t n_passes, double* seconds);
 int mrt_cpu_reset(mrt_cpu_ctx* ctx);

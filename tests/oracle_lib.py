@@ -62,6 +62,9 @@ class OracleSampler(Sampler):
         if self._lib.mrt_cpu_create(C.byref(self._ctx), int(workers), int(n_dim)):
             raise MrtError("mrt_cpu_create failed")
 
+    def set_option(self, option, value):
+        self._check(self._lib.mrt_cpu_set_option(self._ctx, int(option), int(value)))
+
     def set_mode(self, mode):
         self._check(self._lib.mrt_cpu_set_mode(self._ctx, int(mode)))
 

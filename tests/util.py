@@ -32,6 +32,22 @@ def block_mean(a, b=8):
     return a.reshape(h // b, b, w // b, b, -1).mean(axis=(1, 3))
 
 
+def tonemap_f(v, gamma, exp):
+    """sampler.rs:85-94 on float values, scaled to 0..255: `as u8` saturates at 255 and truncates,
+    which lowers the mean of a noisy image by 0.5."""
+    g = np.power(np.maximum(v, 0.0), gamma)
+    t = np.minimum(255.0 * g * (1.0 + g / (1.0 - exp) ** 2) / (1.0 + g), 255.0)
+    return np.maximum(t - 0.5, 0.0)
+
+
+def block_tonemapped(sampler, r, b=8):
+    """Block means of the LINEAR accumulator, then tone-mapped: at a fraction of the reference's
+    spp this avoids the Jensen darkening a noisy image suffers through the concave tone map, so
+    it compares directly with block means of the reference's (converged) PNG."""
+    acc, n = sampler.accum()
+    return tonemap_f(block_mean(acc / n, b), r.frame.cam.gamma, r.frame.cam.exp)
+
+
 def psnr(a, b, peak=255.0):
     mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
     return float("inf") if mse == 0 else 10.0 * np.log10(peak * peak / mse)
