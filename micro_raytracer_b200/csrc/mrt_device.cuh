@@ -38,6 +38,13 @@ struct SlimInst {
     float4 a, b;
 };
 struct Xf { float m[12]; };  // rows of M = rot_y * look (rt.rs:726-727), padded to 3 x float4
+// Two axis-aligned boxes A, B interleaved for the packed FFMA2 slab test (one f32x2 lane each):
+//   q0 = (cA.x, cB.x, cA.y, cB.y)  q1 = (cA.z, cB.z, hA.x, hB.x)  q2 = (hA.y, hB.y, hA.z, hB.z)
+// c = centre, h = half extents.  An odd box count is padded with B = a box of half extents -1,
+// which can never be hit (its t0 > t1 for every ray).
+struct BoxPair { float4 q0, q1, q2; };
+// Rotated box: rows of M with -(M pos)_i in .w  (o_l - pos = M o - M pos), and the half extents.
+struct BxfInst { float4 r0, r1, r2, h; };
 
 enum : uint32_t { FAT_IDENT = 0x100u, FAT_TEX = 0x200u, FAT_NXF = 0x400u /* kind normal goes through M again, rt.rs:792 */ };
 struct FatInst {
@@ -81,22 +88,20 @@ struct SceneCommon {
 };
 struct ParamScene {
     SceneCommon c;
-    SlimInst box[MRT_PB];
+    BoxPair boxp[MRT_PB / 2];
     SlimInst sph[MRT_PS];
     SlimInst pln[MRT_PP];
-    SlimInst bxf[MRT_PX];
-    Xf bxf_m[MRT_PX];
+    BxfInst bxf[MRT_PX];
     SlimInst mesh[MRT_PM];
     Xf mesh_m[MRT_PM];
 };
 static_assert(sizeof(ParamScene) + 256 < 32764, "kernel parameters are limited to 32764 bytes");
 struct GlobalScene {
     SceneCommon c;
-    const SlimInst* box;
+    const BoxPair* boxp;
     const SlimInst* sph;
     const SlimInst* pln;
-    const SlimInst* bxf;
-    const Xf* bxf_m;
+    const BxfInst* bxf;
     const SlimInst* mesh;
     const Xf* mesh_m;
 };
@@ -145,6 +150,15 @@ __device__ __forceinline__ float frcp(float x) {  // one MUFU.RCP
     return r;
 }
 
+// Packed f32x2 arithmetic (sm_100 FFMA2): one issue slot for two FMAs.  Measured on B200
+// (tools/microbench.cu): same 74 TFLOP/s as FFMA in half the issue slots; operands may be
+// register pairs, uniform-register pairs or a scalar broadcast to both lanes.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 bc2(float v) { return pk2(v, v); }
+__device__ __forceinline__ void up2(f2 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
 // Box::intersect's reciprocal with the zero-division workaround, rt.rs:303-316
 __device__ __forceinline__ float rcp_fixed(float d) {
     float m = frcp(d);
@@ -172,11 +186,10 @@ struct ParamView {
     static constexpr bool kParam = true;
     const ParamScene& s;
     __device__ __forceinline__ const SceneCommon& c() const { return s.c; }
-    __device__ __forceinline__ SlimInst box(uint32_t k) const { return s.box[k]; }
+    __device__ __forceinline__ BoxPair boxp(uint32_t k) const { return s.boxp[k]; }
     __device__ __forceinline__ SlimInst sph(uint32_t k) const { return s.sph[k]; }
     __device__ __forceinline__ SlimInst pln(uint32_t k) const { return s.pln[k]; }
-    __device__ __forceinline__ SlimInst bxf(uint32_t k) const { return s.bxf[k]; }
-    __device__ __forceinline__ const Xf& bxf_m(uint32_t k) const { return s.bxf_m[k]; }
+    __device__ __forceinline__ BxfInst bxf(uint32_t k) const { return s.bxf[k]; }
     __device__ __forceinline__ SlimInst mesh(uint32_t k) const { return s.mesh[k]; }
     __device__ __forceinline__ const Xf& mesh_m(uint32_t k) const { return s.mesh_m[k]; }
 };
@@ -185,11 +198,10 @@ struct GlobalView {
     static constexpr bool kParam = false;
     const GlobalScene& s;
     __device__ __forceinline__ const SceneCommon& c() const { return s.c; }
-    __device__ __forceinline__ SlimInst box(uint32_t k) const { return ldg_slim(s.box + k); }
+    __device__ __forceinline__ BoxPair boxp(uint32_t k) const { return {__ldg(&s.boxp[k].q0), __ldg(&s.boxp[k].q1), __ldg(&s.boxp[k].q2)}; }
     __device__ __forceinline__ SlimInst sph(uint32_t k) const { return ldg_slim(s.sph + k); }
     __device__ __forceinline__ SlimInst pln(uint32_t k) const { return ldg_slim(s.pln + k); }
-    __device__ __forceinline__ SlimInst bxf(uint32_t k) const { return ldg_slim(s.bxf + k); }
-    __device__ __forceinline__ const Xf& bxf_m(uint32_t k) const { return s.bxf_m[k]; }
+    __device__ __forceinline__ BxfInst bxf(uint32_t k) const { return {__ldg(&s.bxf[k].r0), __ldg(&s.bxf[k].r1), __ldg(&s.bxf[k].r2), __ldg(&s.bxf[k].h)}; }
     __device__ __forceinline__ SlimInst mesh(uint32_t k) const { return ldg_slim(s.mesh + k); }
     __device__ __forceinline__ const Xf& mesh_m(uint32_t k) const { return s.mesh_m[k]; }
 };
@@ -325,17 +337,30 @@ __device__ __forceinline__ void best_update(Best& B, bool hit, float t0, float t
     }
 }
 
-struct RayPre { f3 o, d, m, nom; };  // m = 1/d (Box::intersect's fix-up applied), nom = -o*m
+struct RayPre { f3 o, d, m, nom, am, nam; };  // m = 1/d (Box::intersect's fix-up applied), nom = -o*m, am = |m|, nam = -|m|
 
 // Box::intersect, rt.rs:299-333, centre/half form: n = (o - pos) m, k = half |m|,
-// t0 = max(-n - k), t1 = min(-n + k); miss iff t0 > t1 or t1 < 0.   9 FFMA + 2 FMNMX3.
+// t0 = max(-n - k), t1 = min(-n + k); miss iff t0 > t1 or t1 < 0.  Two boxes per call, one in
+// each f32x2 lane: 9 FFMA2 + 4 FMNMX3 for the pair.  idx = index of box A (B = idx + 1).
 template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
-__device__ __forceinline__ void test_box(Best& B, const RayPre& r, const SlimInst e, int idx) {
-    const float cx = fmaf(e.a.x, r.m.x, r.nom.x), cy = fmaf(e.a.y, r.m.y, r.nom.y), cz = fmaf(e.a.z, r.m.z, r.nom.z);
-    const float ax = fabsf(r.m.x), ay = fabsf(r.m.y), az = fabsf(r.m.z);
-    const float t0 = fmaxf(fmaxf(fmaf(-e.a.w, ax, cx), fmaf(-e.b.x, ay, cy)), fmaf(-e.b.y, az, cz));
-    const float t1 = fminf(fminf(fmaf(e.a.w, ax, cx), fmaf(e.b.x, ay, cy)), fmaf(e.b.y, az, cz));
-    best_update_slab<F, ANY, WANT_T1, LE>(B, t0, t1, idx);
+__device__ __forceinline__ void test_box_pair(Best& B, const RayPre& r, const BoxPair e, int idx) {
+    const f2 cx = fma2(pk2(e.q0.x, e.q0.y), bc2(r.m.x), bc2(r.nom.x));
+    const f2 cy = fma2(pk2(e.q0.z, e.q0.w), bc2(r.m.y), bc2(r.nom.y));
+    const f2 cz = fma2(pk2(e.q1.x, e.q1.y), bc2(r.m.z), bc2(r.nom.z));
+    const f2 hx = pk2(e.q1.z, e.q1.w), hy = pk2(e.q2.x, e.q2.y), hz = pk2(e.q2.z, e.q2.w);
+    float lxa, lxb, lya, lyb, lza, lzb, hxa, hxb, hya, hyb, hza, hzb;
+    up2(fma2(hx, bc2(r.nam.x), cx), lxa, lxb); up2(fma2(hx, bc2(r.am.x), cx), hxa, hxb);
+    up2(fma2(hy, bc2(r.nam.y), cy), lya, lyb); up2(fma2(hy, bc2(r.am.y), cy), hya, hyb);
+    up2(fma2(hz, bc2(r.nam.z), cz), lza, lzb); up2(fma2(hz, bc2(r.am.z), cz), hza, hzb);
+    const float t0a = fmaxf(fmaxf(lxa, lya), lza), t1a = fminf(fminf(hxa, hya), hza);
+    const float t0b = fmaxf(fmaxf(lxb, lyb), lzb), t1b = fminf(fminf(hxb, hyb), hzb);
+    if constexpr (LE) {  // descending traversal: B first, ties go to the lower index
+        best_update_slab<F, ANY, WANT_T1, LE>(B, t0b, t1b, idx + 1);
+        best_update_slab<F, ANY, WANT_T1, LE>(B, t0a, t1a, idx);
+    } else {
+        best_update_slab<F, ANY, WANT_T1, LE>(B, t0a, t1a, idx);
+        best_update_slab<F, ANY, WANT_T1, LE>(B, t0b, t1b, idx + 1);
+    }
 }
 // Sphere::intersect, rt.rs:335-359, with a = d.d = 1 (directions are unit), half-b form
 template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
@@ -354,15 +379,21 @@ __device__ __forceinline__ void test_plane(Best& B, const RayPre& r, const SlimI
     const float t0 = (e.b.x - dot(r.o, xyz(e.a))) * frcp(dot(r.d, xyz(e.a)));
     best_update<F, ANY, WANT_T1, LE>(B, t0 > 0.0f, t0, t0, idx, -1, -1);
 }
-// rotated box: ray into object space (rt.rs:726-733), slab test about the origin
+// rotated box: ray into object space (rt.rs:726-733), slab test about the origin.  Origin and
+// direction ride in the two f32x2 lanes: (o_l - pos, d_l)_i = M_i0 (o.x, d.x) + M_i1 (o.y, d.y)
+// + M_i2 (o.z, d.z) + (-(M pos)_i, 0): 9 FFMA2 for both transforms.
+struct RayPk { f2 x, y, z; };  // (o.x, d.x), (o.y, d.y), (o.z, d.z)
 template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
-__device__ __forceinline__ void test_bxf(Best& B, const RayPre& r, const SlimInst e, const Xf& x, int idx) {
-    const f3 ol = mulXf(x, r.o - xyz(e.a));
-    const f3 ml = rcp_fixed3(mulXf(x, r.d));
-    const float cx = -ol.x * ml.x, cy = -ol.y * ml.y, cz = -ol.z * ml.z;
+__device__ __forceinline__ void test_bxf(Best& B, const RayPk& p, const BxfInst e, int idx) {
+    float olx, dlx, oly, dly, olz, dlz;
+    up2(fma2(bc2(e.r0.z), p.z, fma2(bc2(e.r0.y), p.y, fma2(bc2(e.r0.x), p.x, pk2(e.r0.w, 0.0f)))), olx, dlx);
+    up2(fma2(bc2(e.r1.z), p.z, fma2(bc2(e.r1.y), p.y, fma2(bc2(e.r1.x), p.x, pk2(e.r1.w, 0.0f)))), oly, dly);
+    up2(fma2(bc2(e.r2.z), p.z, fma2(bc2(e.r2.y), p.y, fma2(bc2(e.r2.x), p.x, pk2(e.r2.w, 0.0f)))), olz, dlz);
+    const f3 ml = rcp_fixed3(mk(dlx, dly, dlz));
+    const float cx = -olx * ml.x, cy = -oly * ml.y, cz = -olz * ml.z;
     const float ax = fabsf(ml.x), ay = fabsf(ml.y), az = fabsf(ml.z);
-    const float t0 = fmaxf(fmaxf(fmaf(-e.b.x, ax, cx), fmaf(-e.b.y, ay, cy)), fmaf(-e.b.z, az, cz));
-    const float t1 = fminf(fminf(fmaf(e.b.x, ax, cx), fmaf(e.b.y, ay, cy)), fmaf(e.b.z, az, cz));
+    const float t0 = fmaxf(fmaxf(fmaf(-e.h.x, ax, cx), fmaf(-e.h.y, ay, cy)), fmaf(-e.h.z, az, cz));
+    const float t1 = fminf(fminf(fmaf(e.h.x, ax, cx), fmaf(e.h.y, ay, cy)), fmaf(e.h.z, az, cz));
     best_update_slab<F, ANY, WANT_T1, LE>(B, t0, t1, idx);
 }
 template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
@@ -401,15 +432,18 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
     r.o = o; r.d = d;
     r.m = rcp_fixed3(d);
     r.nom = mk(-o.x * r.m.x, -o.y * r.m.y, -o.z * r.m.z);
+    r.am = mk(fabsf(r.m.x), fabsf(r.m.y), fabsf(r.m.z));
+    r.nam = -r.am;
+    const RayPk rp = {pk2(o.x, d.x), pk2(o.y, d.y), pk2(o.z, d.z)};
     Best B;
     B.t0 = __int_as_float(0x7f800000); B.t1 = 0.0f; B.bi = -1; B.tr0 = B.tr1 = -1; B.any = false;
 
-#define E_BOX(k, LE) test_box<F, ANY, WANT_T1, LE>(B, r, sc.box(k), (int)(k));
+#define E_BOX(k, LE) test_box_pair<F, ANY, WANT_T1, LE>(B, r, sc.boxp(k), (int)(2u * (k)));
 #define E_SPH(k, LE) test_sphere<F, ANY, WANT_T1, LE>(B, r, sc.sph(k), (int)(c.first[K_SPHERE] + (k)));
 #define E_PLN(k, LE) test_plane<F, ANY, WANT_T1, LE>(B, r, sc.pln(k), (int)(c.first[K_PLANE] + (k)));
-#define E_BXF(k, LE) test_bxf<F, ANY, WANT_T1, LE>(B, r, sc.bxf(k), sc.bxf_m(k), (int)(c.first[K_BOX_XF] + (k)));
+#define E_BXF(k, LE) test_bxf<F, ANY, WANT_T1, LE>(B, rp, sc.bxf(k), (int)(c.first[K_BOX_XF] + (k)));
 #define E_MSH(k, LE) test_mesh<F, ANY, WANT_T1, LE>(B, c, r, sc.mesh(k), sc.mesh_m(k), (int)(c.first[K_MESH] + (k)));
-    MRT_DUFF(c.cnt[K_BOX], E_BOX)
+    MRT_DUFF((c.cnt[K_BOX] + 1u) >> 1, E_BOX)
     MRT_DUFF(c.cnt[K_SPHERE], E_SPH)
     MRT_DUFF(c.cnt[K_PLANE], E_PLN)
     for (uint32_t k = 0; k < c.cnt[K_BOX_XF]; k++) { E_BXF(k, false) }

@@ -1,0 +1,64 @@
+"""Multi-GPU rendering: sample split + one reduce of the accumulation buffers.
+
+The path shards by samples: rank r of G renders the global sample indices
+r, r+G, r+2G, ... of every supersampled pixel, then the per-rank accumulators are summed onto
+`dst` — the only exchange step of the path (it replaces the `Mutex<HashMap>` merge of
+src/sampler.rs:60-70).  One process per GPU; `torch.distributed` is the plumbing (NCCL over
+NVLink for device accumulators; any backend for host accumulators, which is what the
+world-size-2 gloo test on CPU drives).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+
+def passes_of_rank(spp: int, rank: int, world: int) -> int:
+    """How many of the global samples 0..spp-1 rank `rank` renders (indices rank, rank+world, ...)."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError(f"bad partition rank {rank} of {world}")
+    return len(range(rank, spp, world))
+
+
+def reduce_accum(sampler, total_passes: int, group=None, dst: int = 0, device_tensor=None) -> Optional[np.ndarray]:
+    """Sum the samplers' accumulators onto rank `dst` and record there that the buffer now
+    holds `total_passes` passes.
+
+    device_tensor: a torch CUDA tensor aliasing the sampler's device accumulator
+    (torch.as_tensor(sampler.accum_device()[0], device=...)); the reduce then runs in place on
+    the device, ordered on the sampler's stream.  Without it the host accumulator
+    (sampler.accum()) is reduced and the sum is returned on `dst` (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if device_tensor is not None:
+        if world > 1:
+            dist.reduce(device_tensor, dst=dst, op=dist.ReduceOp.SUM, group=group)
+        sampler.set_passes(total_passes)
+        return None
+    acc, _ = sampler.accum()
+    t = torch.from_numpy(np.ascontiguousarray(acc))
+    if world > 1:
+        dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return t.numpy() if rank == dst else None
+
+
+def render_distributed(sampler, scene, frame, rt, spp: int, group=None, dst: int = 0, device_tensor=None):
+    """Render `spp` passes split over the ranks of `group` and reduce onto `dst`.
+    Returns the summed host accumulator on `dst` when no device tensor is given."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    sampler._bind(scene, frame, rt)
+    sampler.reset()
+    sampler.set_partition(rank, world)
+    n = passes_of_rank(spp, rank, world)
+    if device_tensor is not None:
+        sampler.execute_async(n)
+    elif n:
+        sampler.execute(scene, frame, rt, n)
+    return reduce_accum(sampler, spp, group, dst, device_tensor)
