@@ -51,7 +51,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except OSError:
@@ -127,7 +127,7 @@ def workload_config(args, nw, nh):
     return {"workload": f"CornellBox2.json {args.res or 1080}x{args.res or 1080} ssaa2 ({nw}x{nh} film) {args.spp} spp bounce 8 loss 0.15",
             "paths_per_step": nw * nh * args.spp, "parallelism": f"sample-split x{args.gpus} + NCCL reduce" if args.gpus > 1 else "single GPU",
             "l2": "no input reuse across steps: per step the only global traffic is the 74.6 MB accumulator (> L2 share), scene lives in the constant bank",
-            "spp_per_launch": int(os.environ.get("MRT_SPP_PER_LAUNCH", "128"))}
+            "spp_per_launch": args.spp_per_launch}
 
 
 def main():
@@ -141,6 +141,8 @@ def main():
     ap.add_argument("--ref-passes", type=int, default=4, help="passes per step of the CPU reference arm")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spp-per-launch", type=int, default=int(os.environ.get("MRT_SPP_PER_LAUNCH", "1024")),
+                    help="passes rendered by one kernel launch (one accumulator read-modify-write each)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -155,6 +157,7 @@ def main():
     import torch.distributed as dist
 
     import micro_raytracer_b200 as mrt
+    from micro_raytracer_b200.distributed import passes_of_rank, reduce_accum
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback")
@@ -168,7 +171,7 @@ def main():
     r = load_scene(args)
     nw, nh = r.frame.film_size()
     spp = args.spp
-    my_passes = len(range(rank, spp, world))
+    my_passes = passes_of_rank(spp, rank, world)
     packed = mrt.pack_scene(r.scene)
 
     s = mrt.Sampler(device=local_rank)
@@ -179,6 +182,7 @@ def main():
     s.set_stream(stream.cuda_stream)
     s._bind(packed, r.frame, r.rt)
     s.set_partition(rank, world)
+    s.spp_per_launch(args.spp_per_launch)
     acc_dev, _ = s.accum_device()
     acc = torch.as_tensor(acc_dev, device=dev)
 
@@ -190,9 +194,7 @@ def main():
     def render_step():
         s.reset()
         s.execute_async(my_passes)
-        if world > 1:
-            dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
-        s.set_passes(spp)
+        reduce_accum(s, spp, device_tensor=acc)   # NCCL reduce onto rank 0 (no-op at world 1) + pass count
 
     out_img = np.empty((r.frame.res[1], r.frame.res[0], 3), np.uint8)
 
@@ -200,11 +202,15 @@ def main():
         s.set_scene(packed)           # H2D: scene description from host buffers
         s.set_partition(rank, world)
         s.execute_async(my_passes)
-        if world > 1:
-            dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
-        s.set_passes(spp)
+        reduce_accum(s, spp, device_tensor=acc)
         if rank == 0:
             out_img[...] = s.img(r.frame)   # tonemap + Lanczos3 + D2H of the u8 image
+
+    # nvidia-smi takes ~0.5 s to print its first sample: start it before the warm-up, keep only the
+    # samples whose arrival time falls inside the timed region
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
 
     # ---- warm-up
     for _ in range(args.warmup):
@@ -214,8 +220,7 @@ def main():
     # ---- per-launch duration of the dominant kernel (rank-local, CUDA events on the launch stream)
     s.reset()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    spl = int(os.environ.get("MRT_SPP_PER_LAUNCH", "128"))
-    n_launch = -(-my_passes // spl)
+    n_launch = -(-my_passes // s.spp_per_launch())
     ev[0].record(stream)
     s.execute_async(my_passes)
     ev[1].record(stream)
@@ -224,9 +229,6 @@ def main():
     paths_per_launch = nw * nh * my_passes / n_launch
 
     # ---- timed region: K render steps, device timed, clocks sampled
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     barrier()
     l0 = s.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -200,6 +200,11 @@ int mrt_img_ss(mrt_ctx* ctx, uint8_t* rgb);
  * the lens centre (u = 0.5).  out = nw*nh records, row-major. */
 int mrt_trace_primary(mrt_ctx* ctx, mrt_hit* out);
 
+/* Launch granularity of mrt_execute: at most `spp` passes are rendered by one kernel launch
+ * (each launch reads and writes the accumulator once).  Results do not depend on it (the RNG is
+ * keyed by the global sample index); default 1024, env MRT_SPP_PER_LAUNCH.  spp = 0 only queries. */
+int mrt_spp_per_launch(mrt_ctx* ctx, uint32_t spp, uint32_t* current);
+
 /* Counters of the kernels this context launched (bench.py's gpu_launches). */
 int mrt_launch_count(mrt_ctx* ctx, uint64_t* n);
 /* Measured FP32 FMA peak of the device this context lives on, in TFLOP/s

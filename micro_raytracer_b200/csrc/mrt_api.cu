@@ -687,6 +687,13 @@ int mrt_trace_primary(mrt_ctx* c, mrt_hit* out) {
     return MRT_OK;
 }
 
+int mrt_spp_per_launch(mrt_ctx* c, uint32_t spp, uint32_t* current) {
+    if (!c) return MRT_ERR_INVALID;
+    if (spp) c->spp_per_launch = spp;
+    if (current) *current = c->spp_per_launch;
+    return MRT_OK;
+}
+
 int mrt_launch_count(mrt_ctx* c, uint64_t* n) {
     if (!c || !n) return MRT_ERR_INVALID;
     *n = c->launches;

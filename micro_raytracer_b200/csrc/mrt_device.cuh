@@ -476,7 +476,8 @@ __device__ __forceinline__ void load_surf(const FatInst* f, Surf* s) {
         s->m0 = __ldg(&f->m0);
         s->m1 = __ldg(&f->m1);
         s->m2 = __ldg(&f->m2);
-    } else {
+    } else {  // never read (every use is behind !identity() / textured()); initialised because ptxas
+              // allocates 8 registers fewer with it (64 vs 72: one more resident block per SM)
         s->m0 = make_float4(1.f, 0.f, 0.f, __uint_as_float(0xffffffffu));
         s->m1 = make_float4(0.f, 1.f, 0.f, __uint_as_float(0xffffffffu));
         s->m2 = make_float4(0.f, 0.f, 1.f, __uint_as_float(0xffffffffu));
@@ -493,31 +494,34 @@ __device__ __forceinline__ f3 to_local(const Surf& s, f3 hp) {
 // |p_i| equals a window end exactly.)  When no window matches the reference normalises a zero
 // vector (NaN normal, measured 1e-7 of hits); the nearest face is taken instead.
 __device__ __forceinline__ f3 box_face(f3 p) {
-    // distance of |p_i| from 1; a windowed axis gets a negative score that encodes the
-    // reference's priority (z over x over y), otherwise the nearest face wins.  Branch-free.
-    const float ex = fabsf(fabsf(p.x) - 1.0f), ey = fabsf(fabsf(p.y) - 1.0f), ez = fabsf(fabsf(p.z) - 1.0f);
-    const float sz = ez < MRT_E ? -3.0f : ez;
-    const float sx = ex < MRT_E ? -2.0f : ex;
-    const float sy = ey < MRT_E ? -1.0f : ey;
-    const bool fz = sz <= sx && sz <= sy;
-    const bool fx = !fz && sx <= sy;
-    const bool fy = !fz && !fx;
+    const float ex = fabsf(p.x) - 1.0f, ey = fabsf(p.y) - 1.0f, ez = fabsf(p.z) - 1.0f;
+    const bool wx = fabsf(ex) < MRT_E, wy = fabsf(ey) < MRT_E, wz = fabsf(ez) < MRT_E;
+    bool fz = wz, fx = wx && !wz, fy = wy && !wx && !wz;  // z overrides (rt.rs:435), then x, then y
+    if (!(wx || wy || wz)) {  // no window (1e-7 of hits): nearest face instead of the reference's NaN
+        const float ax = fabsf(ex), ay = fabsf(ey), az = fabsf(ez);
+        fz = az <= ax && az <= ay;
+        fx = !fz && ax <= ay;
+        fy = !fz && !fx;
+    }
     return mk(fx ? copysignf(1.0f, p.x) : 0.0f, fy ? copysignf(1.0f, p.y) : 0.0f, fz ? copysignf(1.0f, p.z) : 0.0f);
 }
 // Renderer::normal, rt.rs:776-793: kind normal of the object-space hit point, pushed through
 // the FORWARD transform again (rt.rs:792; unless MRT_NORMAL_OBJECT is selected) and normalised.  Unit inputs through an orthonormal M
 // stay unit to 1e-7, so only mesh normals need the rsqrt.
+template <uint32_t F>
 __device__ __forceinline__ f3 surf_normal(const SceneCommon& c, const Surf& s, f3 pl, int tri) {
     const uint32_t k = s.kind();
     if (k == K_PLANE) return xyz(s.A);  // precomputed norm(M n)
     f3 n;
+    bool mesh = false;
+    if constexpr ((F & F_MESH) != 0) mesh = k == K_MESH;
     if (k == K_SPHERE) n = pl * s.A.x;  // (hit - pos) / r
-    else if (k == K_MESH) {
+    else if (mesh) {
         const DTri* tp = &c.tri[__float_as_uint(s.A.x) + (uint32_t)tri];
         n = cross(xyz(__ldg(&tp->e0)), xyz(__ldg(&tp->e1)));  // rt.rs:459-466
     } else n = box_face(pl * xyz(s.A));
     if (s.normal_xf()) n = mulM(s.m0, s.m1, s.m2, n);  // MRT_OPT_NORMAL_SPACE
-    if (k == K_MESH) n = normalize(n);
+    if (mesh) n = normalize(n);
     return n;
 }
 

@@ -79,7 +79,7 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
         load_surf(fat, &s);
         f3 hp = fma3(d, h.t0, o);
         f3 pl = to_local(s, hp);
-        f3 n = surf_normal(c, s, pl, h.tri0);
+        f3 n = surf_normal<F>(c, s, pl, h.tri0);
         Mat m;
         load_mat<F>(c, fat, s, pl, &m);
 
@@ -114,7 +114,7 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
                     // exit hit: point, normal and material at t1 (rt.rs:886-894)
                     const f3 hp1 = fma3(d, h.t1, o);
                     const f3 pl1 = to_local(s, hp1);
-                    const f3 n1 = surf_normal(c, s, pl1, h.tri1);
+                    const f3 n1 = surf_normal<F>(c, s, pl1, h.tri1);
                     Mat m1;
                     load_mat<F>(c, fat, s, pl1, &m1);
                     // Ray::refract, rt.rs:574-589 ; Vec3f::refract, lin.rs:96-105
@@ -174,12 +174,12 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
 }
 
 template <uint32_t F>
-__global__ void __launch_bounds__(MRT_PATH_BLOCK) path_kernel_param(const __grid_constant__ ParamScene scene,
+__global__ void MRT_PATH_BOUNDS path_kernel_param(const __grid_constant__ ParamScene scene,
                                                                     const __grid_constant__ FilmParams fp) {
     path_body<ParamView, F>(ParamView{scene}, fp);
 }
 template <uint32_t F>
-__global__ void __launch_bounds__(MRT_PATH_BLOCK) path_kernel_global(const __grid_constant__ GlobalScene scene,
+__global__ void MRT_PATH_BOUNDS path_kernel_global(const __grid_constant__ GlobalScene scene,
                                                                      const __grid_constant__ FilmParams fp) {
     path_body<GlobalView, F>(GlobalView{scene}, fp);
 }
@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(128) primary_kernel(const __grid_constant__ Gl
         load_surf(fat, &s);
         const f3 p0 = to_local(s, fma3(d, h.t0, o));
         const f3 p1 = to_local(s, fma3(d, h.t1, o));
-        const f3 n0 = normalize(surf_normal(c, s, p0, h.tri0));
-        const f3 n1 = normalize(surf_normal(c, s, p1, h.tri1));
+        const f3 n0 = normalize(surf_normal<F_ALL>(c, s, p0, h.tri0));
+        const f3 n1 = normalize(surf_normal<F_ALL>(c, s, p1, h.tri1));
         r.t0 = h.t0; r.t1 = h.t1;
         const uint32_t oi = obj_inst[h.inst];
         r.obj = (int)(oi & 0xffffu); r.inst = (int)(oi >> 16);

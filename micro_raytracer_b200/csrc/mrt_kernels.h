@@ -7,6 +7,14 @@
 #ifndef MRT_PATH_BLOCK
 #define MRT_PATH_BLOCK 128
 #endif
+#ifndef MRT_PATH_MINBLOCKS
+#define MRT_PATH_MINBLOCKS 0  // > 0: second __launch_bounds__ argument (forces the register budget)
+#endif
+#if MRT_PATH_MINBLOCKS > 0
+#define MRT_PATH_BOUNDS __launch_bounds__(MRT_PATH_BLOCK, MRT_PATH_MINBLOCKS)
+#else
+#define MRT_PATH_BOUNDS __launch_bounds__(MRT_PATH_BLOCK)
+#endif
 
 struct ParamScene;
 struct GlobalScene;

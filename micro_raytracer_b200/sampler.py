@@ -29,7 +29,8 @@ class MrtError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+    """In-tree libmrt.so; MRT_LIB points at another build of the same library (kernel experiments)."""
+    return os.environ.get("MRT_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 
 def declare(lib, prefix: str = "mrt_"):
@@ -64,6 +65,7 @@ def declare(lib, prefix: str = "mrt_"):
         fn("set_passes", P, u32)
         fn("set_stream", P, P)
         fn("launch_count", P, C.POINTER(u64))
+        fn("spp_per_launch", P, u32, C.POINTER(u32))
         fn("fp32_peak", P, C.POINTER(C.c_double), C.POINTER(C.c_double))
     return lib
 
@@ -239,6 +241,12 @@ class Sampler:
 
     def set_passes(self, passes: int):
         self._check(self._lib.mrt_set_passes(self._ctx, int(passes)))
+
+    def spp_per_launch(self, spp: int = 0) -> int:
+        """Set (spp > 0) or query the number of passes one kernel launch renders."""
+        cur = C.c_uint32()
+        self._check(self._lib.mrt_spp_per_launch(self._ctx, int(spp), C.byref(cur)))
+        return cur.value
 
     def launch_count(self) -> int:
         n = C.c_uint64()

@@ -26,5 +26,5 @@ for i, h in enumerate(hdr):
     if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio"):
         print(f"{h} = {vals[i]}")
 if paths:
-    i = hdr.index("smsp__inst_executed.sum"); j = hdr.index("smsp__thread_inst_executed.sum")
-    print(f"warp-instructions per path x32 = {float(vals[i]) * 32 / paths:.1f}; active thread-instructions per path = {float(vals[j]) / paths:.1f}")
+    i = hdr.index("smsp__inst_executed.sum")
+    print(f"warp-instructions x32 per path = {float(vals[i]) * 32 / paths:.1f}")
