@@ -276,13 +276,14 @@ def main():
             "e2e": {"value": e2e_val, "unit": "Mpaths/s", "h2d_bytes_per_step": packed.nbytes(),
                     "d2h_bytes_per_step": int(out_img.nbytes), "ms_per_step": 1e3 * float(e2e_t.item()) / args.steps},
             "gpu_launches": int(lt.item()),
-            "roofline": {"bound": "fp32", "kernel": "path_kernel_param<0>", "achieved": ach_tf, "peak": peak_tf,
+            "roofline": {"bound": "fp32", "kernel": "path_kernel_jit" if s.jit_status()["launches"] else "path_kernel_param<0>", "achieved": ach_tf, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
                          "peak_source": "FFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
                          "peak_nominal": FP32_NOMINAL_TFLOPS, "frac_of_nominal": ach_tf / FP32_NOMINAL_TFLOPS,
                          "flops_per_path": FLOPS_PER_PATH, "paths_per_launch": paths_per_launch, "launch_ms": launch_ms,
                          "roofline_mpaths_per_gpu": FP32_NOMINAL_TFLOPS * 1e12 / FLOPS_PER_PATH / 1e6},
             "image_mean_u8": float(out_img.mean()),
+            "jit": s.jit_status(),
         }
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):

@@ -156,9 +156,17 @@ int mrt_set_rt(mrt_ctx* ctx, uint32_t bounce, float loss, uint64_t seed);
  *                          ROTATED instance (identity instances are unaffected):
  *     MRT_NORMAL_FORWARD_XF  norm(rot_y * (look * n)) — rt.rs:792 as written at HEAD (default)
  *     MRT_NORMAL_OBJECT      norm(n) — what the revision that rendered doc/out3.png (README's
- *                            CornellBox2 image) did; kept so that golden image stays reproducible. */
-typedef enum mrt_option { MRT_OPT_NORMAL_SPACE = 1 } mrt_option;
+ *                            CornellBox2 image) did; kept so that golden image stays reproducible.
+ *   MRT_OPT_JIT            scene-specialised path kernel: for scenes of <= 64 primitives the library can
+ *                          compile the instance tables INTO the kernel at run time (NVRTC, ~1 s, cached per
+ *                          scene for the life of the process).  Same arithmetic, same results to rounding;
+ *                          only the instruction stream differs (no table loads, no loop control).
+ *     MRT_JIT_AUTO   (default) when one mrt_execute call traces >= 2^26 paths; falls back to the generic
+ *                    kernel if NVRTC is unavailable
+ *     MRT_JIT_OFF    never          MRT_JIT_FORCE   always (error if the compile fails); takes effect at once */
+typedef enum mrt_option { MRT_OPT_NORMAL_SPACE = 1, MRT_OPT_JIT = 2 } mrt_option;
 enum { MRT_NORMAL_FORWARD_XF = 0, MRT_NORMAL_OBJECT = 1 };
+enum { MRT_JIT_OFF = 0, MRT_JIT_AUTO = 1, MRT_JIT_FORCE = 2 };
 int mrt_set_option(mrt_ctx* ctx, uint32_t option, uint32_t value);
 
 /* Multi-GPU sample split: this context renders global sample indices
@@ -204,6 +212,10 @@ int mrt_trace_primary(mrt_ctx* ctx, mrt_hit* out);
  * (each launch reads and writes the accumulator once).  Results do not depend on it (the RNG is
  * keyed by the global sample index); default 1024, env MRT_SPP_PER_LAUNCH.  spp = 0 only queries. */
 int mrt_spp_per_launch(mrt_ctx* ctx, uint32_t spp, uint32_t* current);
+
+/* State of the scene-specialised kernel: eligible (scene small enough), compiled, launches that
+ * used it, NVRTC compile time.  A compile error text is left in mrt_last_error. */
+int mrt_jit_status(mrt_ctx* ctx, uint32_t* eligible, uint32_t* compiled, uint64_t* launches, double* compile_seconds);
 
 /* Counters of the kernels this context launched (bench.py's gpu_launches). */
 int mrt_launch_count(mrt_ctx* ctx, uint64_t* n);

@@ -4,10 +4,12 @@
 // There is no CPU fallback: without a usable CUDA device every compute entry point fails.
 #include "mrt_device.cuh"
 #include "mrt_kernels.h"
+#include "mrt_jit.h"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -119,6 +121,15 @@ struct mrt_ctx {
     uint32_t spp_per_launch = 1024;  // measured: 128 -> 8917, 256 -> 9058, 1024 -> 9234 Mpaths/s (intra-warp tail)
     uint32_t normal_space = MRT_NORMAL_FORWARD_XF;  // MRT_OPT_NORMAL_SPACE
 
+    // run-time scene specialisation (mrt_jit.cu)
+    uint32_t jit_mode = MRT_JIT_AUTO;   // MRT_OPT_JIT
+    std::string jit_header;             // "" = scene not eligible
+    cudaKernel_t jit_kernel = nullptr;  // compiled for jit_header
+    bool jit_tried = false;
+    double jit_seconds = 0.0;
+    std::string jit_err;
+    uint64_t jit_launches = 0;
+
     // film
     DevBuf<float4> d_accum;
     DevBuf<uint8_t> d_ss, d_out;
@@ -207,6 +218,20 @@ void build_leaves(const float* tris, uint32_t n_tri, std::vector<LeafBuild>* out
     }
 }
 
+// float literal that round-trips exactly (C++17 hex float)
+void lit(std::string* o, float v) {
+    char b[48];
+    std::snprintf(b, sizeof b, "%af", (double)v);
+    *o += b;
+}
+void lits(std::string* o, const float* v, int n) {
+    for (int i = 0; i < n; i++) { *o += ", "; lit(o, v[i]); }
+}
+bool all_finite(const float* v, int n) {
+    for (int i = 0; i < n; i++) if (!std::isfinite(v[i])) return false;
+    return true;
+}
+
 uint32_t pack_ids(int32_t lo, int32_t hi) { return ((uint32_t)(lo < 0 ? 0xffff : lo) & 0xffffu) | (((uint32_t)(hi < 0 ? 0xffff : hi) & 0xffffu) << 16); }
 
 }  // namespace
@@ -242,6 +267,10 @@ int mrt_create(mrt_ctx** out, int device, uint32_t workers, uint32_t n_dim) {
     if (const char* s = std::getenv("MRT_SPP_PER_LAUNCH")) {
         const int v = std::atoi(s);
         if (v > 0) c->spp_per_launch = (uint32_t)v;
+    }
+    if (const char* s = std::getenv("MRT_JIT")) {  // default MRT_OPT_JIT of new contexts (experiments, CI)
+        const int v = std::atoi(s);
+        if (v >= 0 && v <= (int)MRT_JIT_FORCE) c->jit_mode = (uint32_t)v;
     }
     c->pscene = new ParamScene();
     *out = c;
@@ -451,6 +480,45 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     CK(c->d_tri.upload(tris));
     CK(c->d_obj_inst.upload(obj_inst));
 
+    // ---- text of the scene for the run-time specialised kernel (mrt_jit.cu); small scenes only
+    c->jit_header.clear();
+    c->jit_kernel = nullptr;
+    c->jit_tried = false;
+    c->jit_err.clear();
+    {
+        const size_t n_prim = 2 * boxp.size() + by_kind[K_SPHERE].size() + by_kind[K_PLANE].size() + bxf.size() + by_kind[K_MESH].size();
+        bool ok = n_prim > 0 && n_prim <= 64;
+        std::string h = "// generated by mrt_set_scene\n";
+        auto tab = [&](const char* name, size_t n, auto&& row) {
+            h += std::string("#define ") + name + "(X)";
+            for (size_t k = 0; k < n; k++) { h += " X(" + std::to_string(k); row(k); h += ")"; }
+            h += "\n";
+        };
+        tab("MRT_JIT_BOXPAIRS", boxp.size(), [&](size_t k) { ok &= all_finite(&boxp[k].q0.x, 12); lits(&h, &boxp[k].q0.x, 12); });
+        tab("MRT_JIT_SPHERES", by_kind[K_SPHERE].size(), [&](size_t k) {
+            const SlimInst& e = by_kind[K_SPHERE][k];
+            const float v[4] = {e.a.x, e.a.y, e.a.z, e.b.x};
+            ok &= all_finite(v, 4); lits(&h, v, 4); });
+        tab("MRT_JIT_PLANES", by_kind[K_PLANE].size(), [&](size_t k) {
+            const SlimInst& e = by_kind[K_PLANE][k];
+            const float v[4] = {e.a.x, e.a.y, e.a.z, e.b.x};
+            ok &= all_finite(v, 4); lits(&h, v, 4); });
+        tab("MRT_JIT_BXFS", bxf.size(), [&](size_t k) { ok &= all_finite(&bxf[k].r0.x, 15); lits(&h, &bxf[k].r0.x, 12); lits(&h, &bxf[k].h.x, 3); });
+        tab("MRT_JIT_MESHES", by_kind[K_MESH].size(), [&](size_t k) {
+            const SlimInst& e = by_kind[K_MESH][k];
+            ok &= all_finite(&e.a.x, 3) && all_finite(mesh_m[k].m, 12);
+            lits(&h, &e.a.x, 3);
+            uint32_t rot, mid;
+            std::memcpy(&rot, &e.b.x, 4); std::memcpy(&mid, &e.b.y, 4);
+            h += ", " + std::to_string(rot) + "u, " + std::to_string(mid) + "u";
+            lits(&h, mesh_m[k].m, 12); });
+        h += "#define MRT_JIT_FIRST_SPHERE " + std::to_string(first[K_SPHERE]) + "\n";
+        h += "#define MRT_JIT_FIRST_PLANE " + std::to_string(first[K_PLANE]) + "\n";
+        h += "#define MRT_JIT_FIRST_BXF " + std::to_string(first[K_BOX_XF]) + "\n";
+        h += "#define MRT_JIT_FIRST_MESH " + std::to_string(first[K_MESH]) + "\n";
+        if (ok) c->jit_header = h;  // the feature mask is appended in mrt_set_scene's tail
+    }
+
     SceneCommon sc{};
     sc.fat = c->d_fat.p; sc.tex = c->d_tex.p; sc.texels = c->d_texels.p;
     sc.mesh = c->d_mesh.p; sc.leaf = c->d_leaf.p; sc.leaf_idx = c->d_leaf_idx.p; sc.tri = c->d_tri.p;
@@ -484,6 +552,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     }
     if (const char* f = std::getenv("MRT_FORCE_FEATURES")) feat |= (uint32_t)std::atoi(f) & F_ALL;
     c->features = feat;
+    if (!c->jit_header.empty()) c->jit_header += "#define MRT_JIT_F " + std::to_string(feat & F_ALL) + "u\n";
     c->have_scene = true;
     return mrt_reset(c);
 }
@@ -514,9 +583,15 @@ int mrt_set_rt(mrt_ctx* c, uint32_t bounce, float loss, uint64_t seed) {
 
 int mrt_set_option(mrt_ctx* c, uint32_t option, uint32_t value) {
     if (!c) return MRT_ERR_INVALID;
-    if (option != MRT_OPT_NORMAL_SPACE || value > MRT_NORMAL_OBJECT) return fail(c, MRT_ERR_INVALID, "unknown option or value");
-    c->normal_space = value;  // read by the next mrt_set_scene
-    return MRT_OK;
+    if (option == MRT_OPT_NORMAL_SPACE && value <= MRT_NORMAL_OBJECT) {
+        c->normal_space = value;  // read by the next mrt_set_scene
+        return MRT_OK;
+    }
+    if (option == MRT_OPT_JIT && value <= MRT_JIT_FORCE) {
+        c->jit_mode = value;
+        return MRT_OK;
+    }
+    return fail(c, MRT_ERR_INVALID, "unknown option or value");
 }
 
 int mrt_set_partition(mrt_ctx* c, uint32_t rank, uint32_t world) {
@@ -531,14 +606,27 @@ int mrt_execute_async(mrt_ctx* c, uint32_t n_passes) {
     if (!c->have_scene || !c->have_frame) return fail(c, MRT_ERR_STATE, "execute before set_scene/set_frame");
     CK(cudaSetDevice(c->device));
     FilmParams fp = make_film_params(c);
+    // Scene-specialised kernel (mrt_jit.cu): compiled on first use when the call is big enough to
+    // amortise ~1 s of NVRTC (MRT_JIT_AUTO), always (MRT_JIT_FORCE) or never (MRT_JIT_OFF).
+    const uint64_t paths = (uint64_t)c->nw * c->nh * n_passes;
+    const bool want_jit = !c->jit_header.empty() &&
+                          (c->jit_mode == MRT_JIT_FORCE || (c->jit_mode == MRT_JIT_AUTO && (paths >= (1ull << 26) || c->jit_kernel)));
+    if (want_jit && !c->jit_tried) {
+        c->jit_tried = true;
+        c->jit_kernel = mrt_jit_kernel(c->jit_header, &c->jit_seconds, &c->jit_err);
+        if (!c->jit_kernel && c->jit_mode == MRT_JIT_FORCE) return fail(c, MRT_ERR_CUDA, "scene specialisation failed: " + c->jit_err);
+    }
+    const bool use_jit = want_jit && c->jit_kernel;
     uint32_t left = n_passes;
     while (left) {
         const uint32_t n = std::min(left, c->spp_per_launch);
         fp.sample0 = c->rank + c->passes * c->world;
         fp.sample_stride = c->world;
         fp.n_samples = n;
-        cudaError_t e = mrt_launch_path(c->features, c->in_param, c->pscene, &c->gscene, fp, c->stream);
+        cudaError_t e = use_jit ? mrt_jit_launch(c->jit_kernel, c->gscene.c, fp, c->stream)
+                                : mrt_launch_path(c->features, c->in_param, c->pscene, &c->gscene, fp, c->stream);
         if (e != cudaSuccess) return cuda_fail(c, e, "path kernel launch");
+        if (use_jit) c->jit_launches++;
         c->launches++;
         c->passes += n;
         c->passes_total += n;
@@ -691,6 +779,16 @@ int mrt_spp_per_launch(mrt_ctx* c, uint32_t spp, uint32_t* current) {
     if (!c) return MRT_ERR_INVALID;
     if (spp) c->spp_per_launch = spp;
     if (current) *current = c->spp_per_launch;
+    return MRT_OK;
+}
+
+int mrt_jit_status(mrt_ctx* c, uint32_t* eligible, uint32_t* compiled, uint64_t* launches, double* compile_seconds) {
+    if (!c) return MRT_ERR_INVALID;
+    if (eligible) *eligible = c->jit_header.empty() ? 0u : 1u;
+    if (compiled) *compiled = c->jit_kernel ? 1u : 0u;
+    if (launches) *launches = c->jit_launches;
+    if (compile_seconds) *compile_seconds = c->jit_seconds;
+    if (!c->jit_err.empty()) c->err = c->jit_err;  // readable through mrt_last_error
     return MRT_OK;
 }
 

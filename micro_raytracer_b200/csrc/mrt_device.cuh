@@ -10,8 +10,16 @@
 //   * FatInst   (128 B/instance = one L1 line): what a lane reads about the ONE instance it
 //     hit (transform, normal data, material); divergent, always global memory.
 #pragma once
+#ifdef __CUDACC_RTC__  // compiled at run time by NVRTC (mrt_jit.cu): no host headers
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+#else
 #include <cstdint>
 #include <cuda_runtime.h>
+#endif
 
 #define MRT_E 0.0001f  // rt.rs:7
 
@@ -184,6 +192,7 @@ __device__ __forceinline__ float4 rng_block(uint32_t pixel, uint32_t sample, uin
 // ------------------------------------------------------------------ scene views
 struct ParamView {
     static constexpr bool kParam = true;
+    static constexpr bool kJit = false;
     const ParamScene& s;
     __device__ __forceinline__ const SceneCommon& c() const { return s.c; }
     __device__ __forceinline__ BoxPair boxp(uint32_t k) const { return s.boxp[k]; }
@@ -196,6 +205,7 @@ struct ParamView {
 __device__ __forceinline__ SlimInst ldg_slim(const SlimInst* p) { return {__ldg(&p->a), __ldg(&p->b)}; }
 struct GlobalView {
     static constexpr bool kParam = false;
+    static constexpr bool kJit = false;
     const GlobalScene& s;
     __device__ __forceinline__ const SceneCommon& c() const { return s.c; }
     __device__ __forceinline__ BoxPair boxp(uint32_t k) const { return {__ldg(&s.boxp[k].q0), __ldg(&s.boxp[k].q1), __ldg(&s.boxp[k].q2)}; }
@@ -204,6 +214,16 @@ struct GlobalView {
     __device__ __forceinline__ BxfInst bxf(uint32_t k) const { return {__ldg(&s.bxf[k].r0), __ldg(&s.bxf[k].r1), __ldg(&s.bxf[k].r2), __ldg(&s.bxf[k].h)}; }
     __device__ __forceinline__ SlimInst mesh(uint32_t k) const { return ldg_slim(s.mesh + k); }
     __device__ __forceinline__ const Xf& mesh_m(uint32_t k) const { return s.mesh_m[k]; }
+};
+
+// Scene-specialised view (mrt_jit.cu): the instance tables are not data at all — the generated
+// header spells every primitive test out with literal operands (MRT_JIT_* X-macros), so the
+// closest-hit "loops" are straight-line code whose constants are FFMA/FFMA2 immediates.
+struct JitView {
+    static constexpr bool kParam = true;
+    static constexpr bool kJit = true;
+    const SceneCommon& s;
+    __device__ __forceinline__ const SceneCommon& c() const { return s; }
 };
 
 // ------------------------------------------------------------------ primitive tests
@@ -438,17 +458,48 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
     Best B;
     B.t0 = __int_as_float(0x7f800000); B.t1 = 0.0f; B.bi = -1; B.tr0 = B.tr1 = -1; B.any = false;
 
+#ifdef MRT_JIT
+    if constexpr (V::kJit) {
+        // ascending declaration order, strict '<': the first minimum wins (rt.rs:872)
+#define J_BOXP(k, a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11) \
+    test_box_pair<F, ANY, WANT_T1, false>(B, r, BoxPair{make_float4(a0, a1, a2, a3), make_float4(a4, a5, a6, a7), make_float4(a8, a9, a10, a11)}, (int)(2 * (k)));
+#define J_SPH(k, cx, cy, cz, r2) \
+    test_sphere<F, ANY, WANT_T1, false>(B, r, SlimInst{make_float4(cx, cy, cz, 0.0f), make_float4(r2, 0.0f, 0.0f, 0.0f)}, (int)(MRT_JIT_FIRST_SPHERE + (k)));
+#define J_PLN(k, nx, ny, nz, off) \
+    test_plane<F, ANY, WANT_T1, false>(B, r, SlimInst{make_float4(nx, ny, nz, 0.0f), make_float4(off, 0.0f, 0.0f, 0.0f)}, (int)(MRT_JIT_FIRST_PLANE + (k)));
+#define J_BXF(k, a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, hx, hy, hz) \
+    test_bxf<F, ANY, WANT_T1, false>(B, rp, BxfInst{make_float4(a0, a1, a2, a3), make_float4(a4, a5, a6, a7), make_float4(a8, a9, a10, a11), make_float4(hx, hy, hz, 0.0f)}, (int)(MRT_JIT_FIRST_BXF + (k)));
+#define J_MSH(k, px, py, pz, rot, mid, m0, m1, m2, m3, m4, m5, m6, m7, m8, m9, m10, m11) \
+    if constexpr ((F & F_MESH) != 0) { const Xf x__ = {{m0, m1, m2, m3, m4, m5, m6, m7, m8, m9, m10, m11}}; \
+        test_mesh<F, ANY, WANT_T1, false>(B, c, r, SlimInst{make_float4(px, py, pz, 0.0f), make_float4(__uint_as_float(rot), __uint_as_float(mid), 0.0f, 0.0f)}, x__, (int)(MRT_JIT_FIRST_MESH + (k))); }
+        MRT_JIT_BOXPAIRS(J_BOXP)
+        MRT_JIT_SPHERES(J_SPH)
+        MRT_JIT_PLANES(J_PLN)
+        MRT_JIT_BXFS(J_BXF)
+        MRT_JIT_MESHES(J_MSH)
+#undef J_BOXP
+#undef J_SPH
+#undef J_PLN
+#undef J_BXF
+#undef J_MSH
+        if constexpr (ANY) return B.any;
+        out->t0 = B.t0; out->t1 = B.t1; out->inst = B.bi; out->tri0 = B.tr0; out->tri1 = B.tr1;
+        return B.bi >= 0;
+    }
+#endif
 #define E_BOX(k, LE) test_box_pair<F, ANY, WANT_T1, LE>(B, r, sc.boxp(k), (int)(2u * (k)));
 #define E_SPH(k, LE) test_sphere<F, ANY, WANT_T1, LE>(B, r, sc.sph(k), (int)(c.first[K_SPHERE] + (k)));
 #define E_PLN(k, LE) test_plane<F, ANY, WANT_T1, LE>(B, r, sc.pln(k), (int)(c.first[K_PLANE] + (k)));
 #define E_BXF(k, LE) test_bxf<F, ANY, WANT_T1, LE>(B, rp, sc.bxf(k), (int)(c.first[K_BOX_XF] + (k)));
 #define E_MSH(k, LE) test_mesh<F, ANY, WANT_T1, LE>(B, c, r, sc.mesh(k), sc.mesh_m(k), (int)(c.first[K_MESH] + (k)));
-    MRT_DUFF((c.cnt[K_BOX] + 1u) >> 1, E_BOX)
-    MRT_DUFF(c.cnt[K_SPHERE], E_SPH)
-    MRT_DUFF(c.cnt[K_PLANE], E_PLN)
-    for (uint32_t k = 0; k < c.cnt[K_BOX_XF]; k++) { E_BXF(k, false) }
-    if constexpr ((F & F_MESH) != 0) {
-        for (uint32_t k = 0; k < c.cnt[K_MESH]; k++) { E_MSH(k, false) }
+    if constexpr (!V::kJit) {
+        MRT_DUFF((c.cnt[K_BOX] + 1u) >> 1, E_BOX)
+        MRT_DUFF(c.cnt[K_SPHERE], E_SPH)
+        MRT_DUFF(c.cnt[K_PLANE], E_PLN)
+        for (uint32_t k = 0; k < c.cnt[K_BOX_XF]; k++) { E_BXF(k, false) }
+        if constexpr ((F & F_MESH) != 0) {
+            for (uint32_t k = 0; k < c.cnt[K_MESH]; k++) { E_MSH(k, false) }
+        }
     }
 #undef E_BOX
 #undef E_SPH

@@ -21,6 +21,7 @@ from .scene import Frame, PackedScene, RayTracer, Scene, pack_scene
 
 _LIB_NAME = "libmrt.so"
 OPT_NORMAL_SPACE, NORMAL_FORWARD_XF, NORMAL_OBJECT = 1, 0, 1  # include/mrt.h
+OPT_JIT, JIT_OFF, JIT_AUTO, JIT_FORCE = 2, 0, 1, 2
 _lib = None
 
 
@@ -66,6 +67,7 @@ def declare(lib, prefix: str = "mrt_"):
         fn("set_stream", P, P)
         fn("launch_count", P, C.POINTER(u64))
         fn("spp_per_launch", P, u32, C.POINTER(u32))
+        fn("jit_status", P, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64), C.POINTER(C.c_double))
         fn("fp32_peak", P, C.POINTER(C.c_double), C.POINTER(C.c_double))
     return lib
 
@@ -247,6 +249,13 @@ class Sampler:
         cur = C.c_uint32()
         self._check(self._lib.mrt_spp_per_launch(self._ctx, int(spp), C.byref(cur)))
         return cur.value
+
+    def jit_status(self) -> dict:
+        """State of the run-time scene-specialised kernel (include/mrt.h: MRT_OPT_JIT)."""
+        e, k, n, t = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_double()
+        self._check(self._lib.mrt_jit_status(self._ctx, C.byref(e), C.byref(k), C.byref(n), C.byref(t)))
+        return {"eligible": bool(e.value), "compiled": bool(k.value), "launches": n.value, "compile_seconds": t.value,
+                "error": (self._lib.mrt_last_error(self._ctx) or b"").decode() if not k.value else ""}
 
     def launch_count(self) -> int:
         n = C.c_uint64()

@@ -21,9 +21,15 @@ CASES = [
 ]
 
 
-@pytest.fixture(scope="module")
-def pair():
-    return mrt.Sampler(device=0), oracle_lib.OracleSampler()
+@pytest.fixture(scope="module", params=["generic", "jit"])
+def pair(request):
+    """Every parity test runs twice: through the offline-compiled generic kernels and through the
+    run-time scene-specialised kernel (MRT_OPT_JIT; scenes of more than 64 primitives stay generic)."""
+    from micro_raytracer_b200.sampler import JIT_FORCE, JIT_OFF, OPT_JIT
+    gpu = mrt.Sampler(device=0)
+    gpu.set_option(OPT_JIT, JIT_FORCE if request.param == "jit" else JIT_OFF)
+    gpu.jit_expected = request.param == "jit"
+    return gpu, oracle_lib.OracleSampler()
 
 
 @pytest.mark.parametrize("name,res,ssaa", CASES)
@@ -76,6 +82,10 @@ def test_shared_rng_paths_match_oracle(pair, name, res, ssaa):
     ac, pc = cpu.accum()
     assert pg == pc == 2
     assert np.isfinite(ag).all()
+    st = gpu.jit_status()
+    assert st["compiled"] == (gpu.jit_expected and st["eligible"]), st
+    if name in ("CornellBox2", "CornellBox", "dof", "Default", "Mesh"):
+        assert st["eligible"]
     ok = np.abs(ag - ac).max(axis=2) <= 1e-3 + 2e-3 * np.abs(ac).max(axis=2)
     assert ok.mean() >= 0.95, f"{name}: only {ok.mean():.4%} pixels match"
     fin = np.isfinite(ac).all(axis=2)
