@@ -189,6 +189,22 @@ __device__ __forceinline__ float4 rng_block(uint32_t pixel, uint32_t sample, uin
     return make_float4((float)(x >> 8) * s, (float)(y >> 8) * s, (float)(z >> 8) * s, (float)(w >> 8) * s);
 }
 
+// Camera block: the 2 lens uniforms of (pixel, sample).  The lens jitter only needs a cheap
+// hash: lowbias32 (Wellons) of the sample index offset by a per-pixel seed, split into two
+// 16-bit uniforms (lens positions on a 65536^2 grid).  Identical in oracle/mrt_oracle.cpp.
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du;
+    x ^= x >> 15; x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t cam_hash_seed(uint32_t pixel, uint32_t key) { return lowbias32(pixel * 0x9E3779B1u + key); }
+__device__ __forceinline__ float2 rng_cam(uint32_t seed, uint32_t sample) {
+    const uint32_t h = lowbias32(seed + sample * 0x85EBCA6Bu);
+    const float s = 1.0f / 65536.0f;
+    return make_float2((float)(h >> 16) * s, (float)(h & 0xffffu) * s);
+}
+
 // ------------------------------------------------------------------ scene views
 struct ParamView {
     static constexpr bool kParam = true;
@@ -545,15 +561,16 @@ __device__ __forceinline__ f3 to_local(const Surf& s, f3 hp) {
 // |p_i| equals a window end exactly.)  When no window matches the reference normalises a zero
 // vector (NaN normal, measured 1e-7 of hits); the nearest face is taken instead.
 __device__ __forceinline__ f3 box_face(f3 p) {
+    // windowed axes get a score that encodes the reference's priority (z over x over y); the rest
+    // score their distance from the face, so the largest score also picks the nearest face when no
+    // window matches.  Branch-free: 3 FADD, 3 FSETP, 3 FSEL, 2 FSETP + PLOP3, 3 LOP3, 3 FSEL.
     const float ex = fabsf(p.x) - 1.0f, ey = fabsf(p.y) - 1.0f, ez = fabsf(p.z) - 1.0f;
-    const bool wx = fabsf(ex) < MRT_E, wy = fabsf(ey) < MRT_E, wz = fabsf(ez) < MRT_E;
-    bool fz = wz, fx = wx && !wz, fy = wy && !wx && !wz;  // z overrides (rt.rs:435), then x, then y
-    if (!(wx || wy || wz)) {  // no window (1e-7 of hits): nearest face instead of the reference's NaN
-        const float ax = fabsf(ex), ay = fabsf(ey), az = fabsf(ez);
-        fz = az <= ax && az <= ay;
-        fx = !fz && ax <= ay;
-        fy = !fz && !fx;
-    }
+    const float sz = fabsf(ez) < MRT_E ? 3.0f : -fabsf(ez);
+    const float sx = fabsf(ex) < MRT_E ? 2.0f : -fabsf(ex);
+    const float sy = fabsf(ey) < MRT_E ? 1.0f : -fabsf(ey);
+    const bool fz = sz >= sx && sz >= sy;
+    const bool fx = !fz && sx >= sy;
+    const bool fy = !fz && !fx;
     return mk(fx ? copysignf(1.0f, p.x) : 0.0f, fy ? copysignf(1.0f, p.y) : 0.0f, fz ? copysignf(1.0f, p.z) : 0.0f);
 }
 // Renderer::normal, rt.rs:776-793: kind normal of the object-space hit point, pushed through

@@ -30,10 +30,11 @@ template <class V, uint32_t F>
 __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
     const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t npix = fp.nw * fp.nh;
-    if (pix >= npix) return;
+    if (pix >= npix || fp.n_samples == 0u) return;
     const uint32_t py = pix / fp.nw, px = pix - py * fp.nw;
     const SceneCommon& c = sc.c();
     const f3 q = pixel_focus_vec(fp, px, py);
+    const uint32_t cam_seed = cam_hash_seed(pix, fp.key);
 
     f3 acc = mk(0.f, 0.f, 0.f);
     f3 o = mk(0.f, 0.f, 0.f), d = mk(0.f, 1.f, 0.f), T = mk(1.f, 1.f, 1.f);
@@ -41,10 +42,17 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
     uint32_t bounce = 0xffffffffu;  // "needs a new camera path"
     uint32_t j = 0;
 
+    // One iteration = one path segment.  A lane whose path ended (miss, emission, bounce limit)
+    // starts its next camera sample at the top of the next iteration and rejoins the warp before
+    // the closest-hit search, so a warp only idles once a lane has rendered all its samples.
+    // Measured alternatives (profiles/): regeneration at the loop tail makes the compiler peel it
+    // into an outer loop (lanes then wait for each other's paths to end); folding the rare miss /
+    // bounce-limit exits into predicated straight-line code costs more issue slots than the
+    // divergent blocks it removes.
     for (;;) {
         if (bounce == 0xffffffffu) {
             if (j >= fp.n_samples) break;
-            const float4 u = rng_block(pix, fp.sample0 + j * fp.sample_stride, 0u, fp.key);
+            const float2 u = rng_cam(cam_seed, fp.sample0 + j * fp.sample_stride);
             camera_ray(fp, q, u.x, u.y, &o, &d);
             T = mk(1.f, 1.f, 1.f);
             pwr = 1.0f;
@@ -62,102 +70,104 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
             bounce = 0xffffffffu; j++;
             continue;
         }
-        const FatInst* fat = c.fat + h.inst;
-        Surf s;
-        load_surf(fat, &s);
-        f3 hp = fma3(d, h.t0, o);
-        f3 pl = to_local(s, hp);
-        f3 n = surf_normal<F>(c, s, pl, h.tri0);
-        Mat m;
-        load_mat<F>(c, fat, s, pl, &m);
-
-        // light visibility from the entry hit, rt.rs:1027-1045 (no distance limit)
-        uint32_t vis = 0;
-        if constexpr ((F & F_LIGHTS) != 0) {
-            for (uint32_t li = 0; li < c.n_lights; li++) {
-                const float4 lv = c.light[li].v_kind;
-                f3 l = (__float_as_uint(lv.w) == 0u) ? normalize(xyz(lv) - hp) : xyz(lv);
-                HitRec dummy;
-                if (!closest_hit<V, F, true, false>(sc, fma3(l, MRT_E, hp), l, &dummy)) vis |= 1u << li;
-            }
-        }
-
-        const float4 u = rng_block(pix, sample, 1u + 2u * bounce, fp.key);
-
-        // Ray::reflect from the entry hit, rt.rs:559-572
-        f3 nd, no;
         {
-            float rough = m.rough;
-            if (m.metal_raw == 0.0f && m.opacity != 0.0f && u.x < 0.80f) rough = 1.0f;
-            const f3 nn = rand_normal(n, rough, u.y, u.z);
-            nd = reflect3(d, nn);  // unit d about unit nn stays unit (the reference's .norm() is a no-op to 1e-7)
-            no = fma3(nd, MRT_E, hp);
-        }
-        // 15 % chance to keep reflecting for transparent material, rt.rs:1051-1059
-        if constexpr ((F & F_TRANSMIT) != 0) {
-            const float p = fminf(1.0f - m.opacity, 0.85f);
-            if (p > 0.0f) {
-                const float4 ub = rng_block(pix, sample, 2u + 2u * bounce, fp.key);
-                if (ub.x < p) {
-                    // exit hit: point, normal and material at t1 (rt.rs:886-894)
-                    const f3 hp1 = fma3(d, h.t1, o);
-                    const f3 pl1 = to_local(s, hp1);
-                    const f3 n1 = surf_normal<F>(c, s, pl1, h.tri1);
-                    Mat m1;
-                    load_mat<F>(c, fat, s, pl1, &m1);
-                    // Ray::refract, rt.rs:574-589 ; Vec3f::refract, lin.rs:96-105
-                    float rough = m1.rough;
-                    if (m1.metal_raw == 0.0f && m1.opacity != 0.0f && ub.y < 0.80f) rough = 1.0f;
-                    const f3 nn = rand_normal(n1, rough, ub.z, ub.w);
-                    const float eta = 1.0f + 0.5f * m1.glass;
-                    const float cs = -dot(nn, d);
-                    const float k = 1.0f - eta * eta * (1.0f - cs * cs);
-                    if (k >= 0.0f) {
-                        const f3 rd = normalize(fma3(nn, cs * eta + sqrtf(k), d * eta));
-                        nd = rd;
-                        no = fma3(rd, MRT_E, hp1);
-                        hp = hp1; n = n1; m = m1;  // the recorded hit is the exit hit
+            const FatInst* fat = c.fat + h.inst;
+            Surf s;
+            load_surf(fat, &s);
+            f3 hp = fma3(d, h.t0, o);
+            f3 pl = to_local(s, hp);
+            f3 n = surf_normal<F>(c, s, pl, h.tri0);
+            Mat m;
+            load_mat<F>(c, fat, s, pl, &m);
+
+            // light visibility from the entry hit, rt.rs:1027-1045 (no distance limit)
+            uint32_t vis = 0;
+            if constexpr ((F & F_LIGHTS) != 0) {
+                for (uint32_t li = 0; li < c.n_lights; li++) {
+                    const float4 lv = c.light[li].v_kind;
+                    f3 l = (__float_as_uint(lv.w) == 0u) ? normalize(xyz(lv) - hp) : xyz(lv);
+                    HitRec dummy;
+                    if (!closest_hit<V, F, true, false>(sc, fma3(l, MRT_E, hp), l, &dummy)) vis |= 1u << li;
+                }
+            }
+
+            const float4 u = rng_block(pix, sample, 1u + 2u * bounce, fp.key);
+
+            // Ray::reflect from the entry hit, rt.rs:559-572
+            f3 nd, no;
+            {
+                float rough = m.rough;
+                if (m.metal_raw == 0.0f && m.opacity != 0.0f && u.x < 0.80f) rough = 1.0f;
+                const f3 nn = rand_normal(n, rough, u.y, u.z);
+                nd = reflect3(d, nn);  // unit d about unit nn stays unit (the reference's .norm() is a no-op to 1e-7)
+                no = fma3(nd, MRT_E, hp);
+            }
+            // 15 % chance to keep reflecting for transparent material, rt.rs:1051-1059
+            if constexpr ((F & F_TRANSMIT) != 0) {
+                const float p = fminf(1.0f - m.opacity, 0.85f);
+                if (p > 0.0f) {
+                    const float4 ub = rng_block(pix, sample, 2u + 2u * bounce, fp.key);
+                    if (ub.x < p) {
+                        // exit hit: point, normal and material at t1 (rt.rs:886-894)
+                        const f3 hp1 = fma3(d, h.t1, o);
+                        const f3 pl1 = to_local(s, hp1);
+                        const f3 n1 = surf_normal<F>(c, s, pl1, h.tri1);
+                        Mat m1;
+                        load_mat<F>(c, fat, s, pl1, &m1);
+                        // Ray::refract, rt.rs:574-589 ; Vec3f::refract, lin.rs:96-105
+                        float rough = m1.rough;
+                        if (m1.metal_raw == 0.0f && m1.opacity != 0.0f && ub.y < 0.80f) rough = 1.0f;
+                        const f3 nn = rand_normal(n1, rough, ub.z, ub.w);
+                        const float eta = 1.0f + 0.5f * m1.glass;
+                        const float cs = -dot(nn, d);
+                        const float k = 1.0f - eta * eta * (1.0f - cs * cs);
+                        if (k >= 0.0f) {
+                            const f3 rd = normalize(fma3(nn, cs * eta + sqrtf(k), d * eta));
+                            nd = rd;
+                            no = fma3(rd, MRT_E, hp1);
+                            hp = hp1; n = n1; m = m1;  // the recorded hit is the exit hit
+                        }
                     }
                 }
             }
-        }
 
-        // ---- RayTracer::reduce_light, rt.rs:956-994, evaluated forward
-        if (u.w < m.emit) {  // emission draw, rt.rs:966-970
-            acc = acc + T * m.color;
-            bounce = 0xffffffffu; j++;
-            continue;
-        }
-        if constexpr ((F & F_LIGHTS) != 0) {
-            f3 lc = mk(0.f, 0.f, 0.f);
-            for (uint32_t li = 0; li < c.n_lights; li++) {
-                if (!((vis >> li) & 1u)) continue;
-                const float4 lv = c.light[li].v_kind;
-                const float4 cp = c.light[li].color_pwr;
-                const f3 l = (__float_as_uint(lv.w) == 0u) ? normalize(xyz(lv) - hp) : xyz(lv);
-                const float diff = fmaxf(dot(l, n), 0.0f);
-                float sp = fmaxf(dot(d, reflect3(l, n)), 0.0f);
-                sp *= sp; sp *= sp; sp *= sp; sp *= sp; sp *= sp;  // powi(32), rt.rs:981
-                sp *= (1.0f - m.rough);
-                const f3 oc = m.color * ((1.0f - m.metal) * diff);
-                lc = lc + mk(fmaf(oc.x, cp.x, sp), fmaf(oc.y, cp.y, sp), fmaf(oc.z, cp.z, sp)) * cp.w;
+            // ---- RayTracer::reduce_light, rt.rs:956-994, evaluated forward
+            if (u.w < m.emit) {  // emission draw, rt.rs:966-970
+                acc = acc + T * m.color;
+                bounce = 0xffffffffu; j++;
+                continue;
             }
-            acc = acc + T * (lc * pwr);
-        }
-        T = T * mk((0.5f + m.color.x) * pwr, (0.5f + m.color.y) * pwr, (0.5f + m.color.z) * pwr);  // rt.rs:990-992
-
-        o = no; d = nd;
-        pwr *= fp.keep;
-        bounce++;
-        // a NaN direction (|n + r v| = 0) would poison the lane: end the path as a miss
-        const bool bad = !(fabsf(d.x) <= 2.0f);
-        if (bounce > fp.max_bounce || bad) {  // rt.rs:1018
-            acc = acc + T * mk(c.sky_tail[0], c.sky_tail[1], c.sky_tail[2]);
-            bounce = 0xffffffffu; j++;
+            {
+                if constexpr ((F & F_LIGHTS) != 0) {
+                    f3 lc = mk(0.f, 0.f, 0.f);
+                    for (uint32_t li = 0; li < c.n_lights; li++) {
+                        if (!((vis >> li) & 1u)) continue;
+                        const float4 lv = c.light[li].v_kind;
+                        const float4 cp = c.light[li].color_pwr;
+                        const f3 l = (__float_as_uint(lv.w) == 0u) ? normalize(xyz(lv) - hp) : xyz(lv);
+                        const float diff = fmaxf(dot(l, n), 0.0f);
+                        float sp = fmaxf(dot(d, reflect3(l, n)), 0.0f);
+                        sp *= sp; sp *= sp; sp *= sp; sp *= sp; sp *= sp;  // powi(32), rt.rs:981
+                        sp *= (1.0f - m.rough);
+                        const f3 oc = m.color * ((1.0f - m.metal) * diff);
+                        lc = lc + mk(fmaf(oc.x, cp.x, sp), fmaf(oc.y, cp.y, sp), fmaf(oc.z, cp.z, sp)) * cp.w;
+                    }
+                    acc = acc + T * (lc * pwr);
+                }
+                T = T * mk((0.5f + m.color.x) * pwr, (0.5f + m.color.y) * pwr, (0.5f + m.color.z) * pwr);  // rt.rs:990-992
+                o = no; d = nd;
+                pwr *= fp.keep;
+                bounce++;
+                // a NaN direction (|n + r v| = 0) would poison the lane: end the path as a miss
+                const bool bad = !(fabsf(d.x) <= 2.0f);
+                if (bounce > fp.max_bounce || bad) {  // rt.rs:1018
+                    acc = acc + T * mk(c.sky_tail[0], c.sky_tail[1], c.sky_tail[2]);
+                    bounce = 0xffffffffu; j++;
+                }
+            }
         }
     }
     float4 a = fp.accum[pix];
     a.x += acc.x; a.y += acc.y; a.z += acc.z;
     fp.accum[pix] = a;
 }
-

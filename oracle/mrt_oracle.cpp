@@ -130,12 +130,29 @@ inline Block rng_block(uint32_t pixel, uint32_t sample, uint32_t block, uint32_t
     for (int i = 0; i < 4; i++) b.u[i] = (float)(v[i] >> 8) * (1.0f / 16777216.0f);  // U[0,1), 24 bit
     return b;
 }
-// block ids: 0 = camera (u0,u1 lens); 1+2b = bounce b "A" (u0 reflect lottery, u1,u2 reflect
+// camera block: lowbias32 (Wellons) of the sample index offset by a per-pixel seed, split into
+// two 16-bit uniforms (the lens jitter only needs a cheap hash)
+inline uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du;
+    x ^= x >> 15; x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+inline Block rng_cam(uint32_t pixel, uint32_t sample, uint32_t key) {
+    const uint32_t seed = lowbias32(pixel * 0x9E3779B1u + key);
+    const uint32_t h = lowbias32(seed + sample * 0x85EBCA6Bu);
+    Block b;
+    b.u[0] = (float)(h >> 16) * (1.0f / 65536.0f);
+    b.u[1] = (float)(h & 0xffffu) * (1.0f / 65536.0f);
+    b.u[2] = b.u[3] = 0.0f;
+    return b;
+}
+// block ids: camera = rng_cam (u0,u1 lens); 1+2b = bounce b "A" (u0 reflect lottery, u1,u2 reflect
 // direction, u3 emission draw); 2+2b = bounce b "B" (u0 transmission lottery, u1 refract
 // lottery, u2,u3 refract direction).
 struct PathRng {
     uint32_t pixel, sample, key;
-    Block cam() const { return rng_block(pixel, sample, 0u, key); }
+    Block cam() const { return rng_cam(pixel, sample, key); }
     Block a(uint32_t bounce) const { return rng_block(pixel, sample, 1u + 2u * bounce, key); }
     Block b(uint32_t bounce) const { return rng_block(pixel, sample, 2u + 2u * bounce, key); }
 };
