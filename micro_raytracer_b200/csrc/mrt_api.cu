@@ -125,7 +125,7 @@ struct mrt_ctx {
     uint32_t jit_mode = MRT_JIT_AUTO;   // MRT_OPT_JIT
     std::string jit_header;             // "" = scene not eligible
     cudaKernel_t jit_kernel = nullptr;  // compiled for jit_header
-    bool jit_tried = false;
+    bool jit_requested = false, jit_failed = false, jit_from_disk = false;
     double jit_seconds = 0.0;
     std::string jit_err;
     uint64_t jit_launches = 0;
@@ -281,6 +281,7 @@ void mrt_destroy(mrt_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->jit_requested && !c->jit_header.empty()) mrt_jit_wait(c->jit_header);
     for (auto& b : c->d_slim) b.release();
     c->d_boxp.release(); c->d_bxf.release(); c->d_mesh_m.release(); c->d_fat.release(); c->d_tex.release(); c->d_texels.release();
     c->d_mesh.release(); c->d_leaf.release(); c->d_leaf_idx.release(); c->d_tri.release(); c->d_obj_inst.release();
@@ -482,8 +483,9 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
 
     // ---- text of the scene for the run-time specialised kernel (mrt_jit.cu); small scenes only
     c->jit_header.clear();
+    if (c->jit_requested && !c->jit_header.empty()) mrt_jit_wait(c->jit_header);  // never abandon a running compile
     c->jit_kernel = nullptr;
-    c->jit_tried = false;
+    c->jit_requested = c->jit_failed = c->jit_from_disk = false;
     c->jit_err.clear();
     {
         const size_t n_prim = 2 * boxp.size() + by_kind[K_SPHERE].size() + by_kind[K_PLANE].size() + bxf.size() + by_kind[K_MESH].size();
@@ -606,15 +608,23 @@ int mrt_execute_async(mrt_ctx* c, uint32_t n_passes) {
     if (!c->have_scene || !c->have_frame) return fail(c, MRT_ERR_STATE, "execute before set_scene/set_frame");
     CK(cudaSetDevice(c->device));
     FilmParams fp = make_film_params(c);
-    // Scene-specialised kernel (mrt_jit.cu): compiled on first use when the call is big enough to
-    // amortise ~1 s of NVRTC (MRT_JIT_AUTO), always (MRT_JIT_FORCE) or never (MRT_JIT_OFF).
+    // Scene-specialised kernel (mrt_jit.cu).  MRT_JIT_AUTO never stalls a small call: the first
+    // execute after set_scene starts the NVRTC compile on a background thread (or finds the cubin in
+    // the process / on-disk cache) and this and later calls switch over as soon as it is ready; a call
+    // big enough to amortise the ~0.15 s compile (>= 2^33 paths) waits for it.  MRT_JIT_FORCE waits.
     const uint64_t paths = (uint64_t)c->nw * c->nh * n_passes;
-    const bool want_jit = !c->jit_header.empty() &&
-                          (c->jit_mode == MRT_JIT_FORCE || (c->jit_mode == MRT_JIT_AUTO && (paths >= (1ull << 26) || c->jit_kernel)));
-    if (want_jit && !c->jit_tried) {
-        c->jit_tried = true;
-        c->jit_kernel = mrt_jit_kernel(c->jit_header, &c->jit_seconds, &c->jit_err);
-        if (!c->jit_kernel && c->jit_mode == MRT_JIT_FORCE) return fail(c, MRT_ERR_CUDA, "scene specialisation failed: " + c->jit_err);
+    const bool want_jit = !c->jit_header.empty() && c->jit_mode != MRT_JIT_OFF;
+    if (want_jit && !c->jit_kernel && !c->jit_failed) {
+        MrtJitInfo info;
+        c->jit_kernel = mrt_jit_kernel(c->jit_header, c->jit_mode == MRT_JIT_FORCE || paths >= (1ull << 33), &info);
+        c->jit_requested = true;
+        if (!info.pending) {
+            c->jit_seconds = info.seconds;
+            c->jit_from_disk = info.from_disk;
+            c->jit_err = info.err;
+            c->jit_failed = !c->jit_kernel;
+            if (c->jit_failed && c->jit_mode == MRT_JIT_FORCE) return fail(c, MRT_ERR_CUDA, "scene specialisation failed: " + c->jit_err);
+        }
     }
     const bool use_jit = want_jit && c->jit_kernel;
     uint32_t left = n_passes;
@@ -784,10 +794,11 @@ int mrt_spp_per_launch(mrt_ctx* c, uint32_t spp, uint32_t* current) {
 
 int mrt_jit_status(mrt_ctx* c, uint32_t* eligible, uint32_t* compiled, uint64_t* launches, double* compile_seconds) {
     if (!c) return MRT_ERR_INVALID;
+    if (compile_seconds && c->jit_from_disk) *compile_seconds = -c->jit_seconds;  // negative: loaded from the disk cache
     if (eligible) *eligible = c->jit_header.empty() ? 0u : 1u;
     if (compiled) *compiled = c->jit_kernel ? 1u : 0u;
     if (launches) *launches = c->jit_launches;
-    if (compile_seconds) *compile_seconds = c->jit_seconds;
+    if (compile_seconds && !c->jit_from_disk) *compile_seconds = c->jit_seconds;
     if (!c->jit_err.empty()) c->err = c->jit_err;  // readable through mrt_last_error
     return MRT_OK;
 }

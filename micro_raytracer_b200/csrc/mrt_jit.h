@@ -6,8 +6,13 @@
 
 #include "mrt_device.cuh"
 
-// Compiles (or fetches from the process-wide cache) the kernel specialised for `scene_header`
-// (the text mrt_api.cu generates: feature mask + instance tables as literal X-macro lists).
-// Returns nullptr when NVRTC is unavailable or the compile failed (*err says why).
-cudaKernel_t mrt_jit_kernel(const std::string& scene_header, double* compile_seconds, std::string* err);
+struct MrtJitInfo { bool pending = false; bool from_disk = false; double seconds = 0.0; std::string err; };
+
+// The kernel specialised for `scene_header` (the text mrt_api.cu generates: feature mask + instance
+// tables as literal X-macro lists).  The first request starts an NVRTC compile on a background thread
+// (or loads the cubin from the on-disk cache); wait = true blocks until it is over.  Returns nullptr
+// while the compile is pending, when NVRTC is unavailable, or when the compile failed (info->err).
+cudaKernel_t mrt_jit_kernel(const std::string& scene_header, bool wait, MrtJitInfo* info);
+// Blocks until a compile started for `scene_header` (if any) is over.
+void mrt_jit_wait(const std::string& scene_header);
 cudaError_t mrt_jit_launch(cudaKernel_t k, const SceneCommon& scene, const FilmParams& fp, cudaStream_t st);

@@ -254,7 +254,8 @@ class Sampler:
         """State of the run-time scene-specialised kernel (include/mrt.h: MRT_OPT_JIT)."""
         e, k, n, t = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_double()
         self._check(self._lib.mrt_jit_status(self._ctx, C.byref(e), C.byref(k), C.byref(n), C.byref(t)))
-        return {"eligible": bool(e.value), "compiled": bool(k.value), "launches": n.value, "compile_seconds": t.value,
+        return {"eligible": bool(e.value), "compiled": bool(k.value), "launches": n.value, "compile_seconds": abs(t.value),
+                "from_disk_cache": t.value < 0,
                 "error": (self._lib.mrt_last_error(self._ctx) or b"").decode() if not k.value else ""}
 
     def launch_count(self) -> int:

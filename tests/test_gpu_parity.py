@@ -1,5 +1,7 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the
 same seeded inputs.  Run with `-m gpu` on the B200 box."""
+import os
+
 import numpy as np
 import pytest
 
@@ -239,3 +241,39 @@ def test_golden_out2_out4_stochastic_renders():
         for c in range(3):
             assert abs(img[..., c].mean() - ref[..., c].mean()) <= 0.01 * ref[..., c].mean(), ref_name
         assert psnr(block_mean(img), block_mean(ref)) >= db, ref_name
+
+
+def test_jit_auto_compiles_in_the_background_and_switches_over(tmp_path, monkeypatch):
+    """MRT_JIT_AUTO: pass-by-pass calls (the reference's `for sample in 0..n { execute }` loop,
+    cli.rs:162) never wait for NVRTC; they switch to the specialised kernel once it is ready, and
+    the image is the same as the generic kernel's up to rounding (same RNG, same arithmetic)."""
+    import time
+    from micro_raytracer_b200.sampler import JIT_AUTO, JIT_OFF, OPT_JIT
+    monkeypatch.setenv("MRT_JIT_CACHE", str(tmp_path))  # a cold on-disk cache
+    r = load("CornellBox", (96, 54), 1.0)
+    r.scene.renderer[0].mat.albedo = (0.7311, 0.7312, 0.7313)  # a scene no other test compiled in this process
+    a, b = mrt.Sampler(device=0), mrt.Sampler(device=0)
+    a.set_option(OPT_JIT, JIT_AUTO)
+    b.set_option(OPT_JIT, JIT_OFF)
+    t_first = time.perf_counter()
+    a.execute(r.scene, r.frame, r.rt, 1)
+    t_first = time.perf_counter() - t_first
+    n = 1
+    while not a.jit_status()["compiled"] and n < 400:
+        a.execute(r.scene, r.frame, r.rt, 1)
+        n += 1
+        time.sleep(0.01)
+    st = a.jit_status()
+    assert st["compiled"] and not st["from_disk_cache"], st
+    a.execute(r.scene, r.frame, r.rt, 3)
+    n += 3
+    assert a.jit_status()["launches"] >= 2  # the switch-over call(s) + this one
+    assert t_first < 0.5 * max(st["compile_seconds"], 0.05) + 0.05, (t_first, st)  # the first call did not wait
+    b.execute(r.scene, r.frame, r.rt, n)
+    ia, ib = a.accum()[0], b.accum()[0]
+    ok = np.abs(ia - ib).max(axis=2) <= 1e-4 + 1e-4 * np.abs(ib).max(axis=2)
+    assert ok.mean() >= 0.99
+    assert any(f.endswith(".cubin") for f in os.listdir(tmp_path))  # published for the next process
+    c = mrt.Sampler(device=0)  # same process: served from the in-memory cache at once
+    c.execute(r.scene, r.frame, r.rt, 1)
+    assert c.jit_status()["compiled"]

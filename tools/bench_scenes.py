@@ -1,0 +1,49 @@
+"""Throughput of every BASELINE.json config (not the headline bench): Mpaths/s per scene on one GPU,
+render-only (CUDA-event seconds returned by mrt_execute), at the configs' full resolutions with a
+bounded number of passes; optionally the oracle's rate on the host cores beside it.
+    python tools/bench_scenes.py [--cpu]
+"""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import micro_raytracer_b200 as mrt
+from util import load
+
+# (label, scene, res, ssaa, rt overrides, passes timed here)
+CONFIGS = [
+    ("1 Default 1280x720 direct light", "Default", None, None, {}, 256),
+    ("2 CornellBox2 1080^2 ssaa2 (headline)", "CornellBox2", None, None, {}, 256),
+    ("3 CornellBox (README 10-object) 1920x1080 bounce16", "CornellBox", (1920, 1080), 1.0, {"bounce": 16}, 256),
+    ("4a Mesh 1920x1080", "Mesh", (1920, 1080), 1.0, {}, 32),
+    ("4b Instance (1000 spheres) 1920x1080", "Instance", (1920, 1080), 1.0, {}, 16),
+    ("5a Minecraft 3840x2160 ssaa2", "Minecraft", (3840, 2160), 2.0, {}, 8),
+    ("5b dof 3840x2160", "dof", (3840, 2160), 1.0, {}, 64),
+]
+
+def main():
+    cpu = "--cpu" in sys.argv
+    rows = []
+    for label, name, res, ssaa, rt, passes in CONFIGS:
+        r = load(name, res, ssaa, **rt)
+        s = mrt.Sampler(device=0)
+        s.execute(r.scene, r.frame, r.rt, 1)  # upload + warm-up (+ JIT compile when eligible: needs a big call)
+        nw, nh, _ = s.film_size()
+        s.reset()
+        sec = s.execute(r.scene, r.frame, r.rt, passes)
+        sec = min(sec, s.execute(r.scene, r.frame, r.rt, passes))
+        row = {"config": label, "film": [nw, nh], "passes": passes, "gpu_mpaths_s": nw * nh * passes / sec / 1e6,
+               "jit": s.jit_status()["launches"] > 0}
+        if cpu:
+            import oracle_lib
+            c = oracle_lib.OracleSampler(workers=0)
+            r2 = load(name, (max(1, r.frame.res[0] // 4), max(1, r.frame.res[1] // 4)), ssaa, **rt)
+            t = c.execute(r2.scene, r2.frame, r2.rt, 1)
+            w2, h2, _ = c.film_size()
+            row["cpu_mpaths_s"] = w2 * h2 / t / 1e6
+            row["cpu_cores"] = os.cpu_count()
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+    return rows
+
+if __name__ == "__main__":
+    main()
