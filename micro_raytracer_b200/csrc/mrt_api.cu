@@ -183,7 +183,7 @@ FilmParams make_film_params(const mrt_ctx* c) {
 // child order (rt.rs:631-689, parser.rs:805-824), each with the triangles that have a vertex
 // inside it (rt.rs:227-248).
 struct LeafBuild { H3 center, size; std::vector<uint32_t> idx; };
-void build_leaves(const float* tris, uint32_t n_tri, std::vector<LeafBuild>* out) {
+void build_leaves(const float* tris, uint32_t n_tri, std::vector<LeafBuild>* out, float root_half[3]) {
     static const float G[8][3] = {{1, 1, 1}, {-1, 1, 1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, -1}, {1, -1, -1}};
     float mx = 0, my = 0, mz = 0;  // Mesh::gen_aabb, rt.rs:261-270
     for (uint32_t t = 0; t < n_tri; t++)
@@ -192,6 +192,7 @@ void build_leaves(const float* tris, uint32_t n_tri, std::vector<LeafBuild>* out
             mx = std::fmax(mx, std::fabs(p[0])); my = std::fmax(my, std::fabs(p[1])); mz = std::fmax(mz, std::fabs(p[2]));
         }
     const H3 A0 = {2.0f * mx, 2.0f * my, 2.0f * mz};
+    root_half[0] = 0.5f * A0.x; root_half[1] = 0.5f * A0.y; root_half[2] = 0.5f * A0.z;  // Box::intersect halves the size, rt.rs:318
     const H3 A1 = {0.5f * A0.x, 0.5f * A0.y, 0.5f * A0.z};
     const H3 A2 = {0.5f * A1.x, 0.5f * A1.y, 0.5f * A1.z};
     const H3 A3 = {0.5f * A2.x, 0.5f * A2.y, 0.5f * A2.z};
@@ -338,9 +339,10 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
         if (m.n_tri == 0) return fail(c, MRT_ERR_INVALID, "empty mesh");
         const float* tp = s->triangles + 9 * (size_t)m.first_tri;
         std::vector<LeafBuild> lb;
-        build_leaves(tp, m.n_tri, &lb);
+        float root_half[3];
+        build_leaves(tp, m.n_tri, &lb, root_half);
         if (lb.empty()) return fail(c, MRT_ERR_INVALID, "mesh octree is empty (the reference would panic, rt.rs:717)");
-        meshes[i] = {(uint32_t)leaves.size(), (uint32_t)lb.size(), (uint32_t)tris.size(), m.n_tri};
+        meshes[i] = {(uint32_t)leaves.size(), (uint32_t)lb.size(), (uint32_t)tris.size(), m.n_tri, {root_half[0], root_half[1], root_half[2]}, 0.0f};
         for (const LeafBuild& l : lb) {
             DMeshLeaf dl;
             dl.lo = make_float4(l.center.x - 0.5f * l.size.x, l.center.y - 0.5f * l.size.y, l.center.z - 0.5f * l.size.z, u2f((uint32_t)leaf_idx.size()));
@@ -489,7 +491,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     c->jit_err.clear();
     {
         const size_t n_prim = 2 * boxp.size() + by_kind[K_SPHERE].size() + by_kind[K_PLANE].size() + bxf.size() + by_kind[K_MESH].size();
-        bool ok = n_prim > 0 && n_prim <= 64;
+        bool ok = n_prim > 0 && n_prim <= 128;
         std::string h = "// generated by mrt_set_scene\n";
         auto tab = [&](const char* name, size_t n, auto&& row) {
             h += std::string("#define ") + name + "(X)";

@@ -68,7 +68,7 @@ static_assert(sizeof(FatInst) == 128, "FatInst must be one cache line");
 struct DLight { float4 v_kind; float4 color_pwr; };  // v.xyz (pos or unit -dir), w = kind bits ; color.rgb, pwr
 struct DTex { uint32_t w, h, first, has_dat; };      // texel offset into the float4 texel array
 struct DMeshLeaf { float4 lo, hi; };                  // leaf box relative to instance pos; lo.w = first index (bits), hi.w = count (bits)
-struct DMesh { uint32_t first_leaf, n_leaf, first_tri, n_tri; };
+struct DMesh { uint32_t first_leaf, n_leaf, first_tri, n_tri; float half[3]; float _pad; };  // half = half extents of the root AABB
 struct DTri { float4 v0, e0, e1; };                   // v0, e0 = v1 - v0, e1 = v2 - v0 (object space, before + pos)
 
 // capacities of the kernel-parameter scene (constant bank); larger scenes use GlobalScene
@@ -262,29 +262,56 @@ __device__ __forceinline__ bool tri_test(const DTri& tr, f3 o_rel /* ray.orig - 
     return true;
 }
 
-// Mesh leg of Renderer::intersect, rt.rs:740-772, over the flattened depth-3 octree: every
-// non-empty leaf the ray pierces contributes its triangle list (rt.rs:707-723); entry = first
-// minimum t, exit = last maximum t.  o_rel = object-space origin minus instance pos.
+// Mesh leg of Renderer::intersect, rt.rs:740-772, over the flattened depth-3 octree: the root box
+// must be pierced (rt.rs:708-710), then every non-empty leaf the ray pierces contributes its triangle
+// list (rt.rs:707-723); entry = first minimum t, exit = last maximum t.  o_rel = object-space origin
+// minus instance pos.
+//
+// Two phases per chunk of 32 leaves, because the lanes of a warp pierce different leaves: (1) all
+// lanes slab-test the chunk's leaves in lockstep and keep a bit per pierced leaf; (2) every lane
+// walks ITS OWN pierced leaves and tests one triangle per iteration, so the warp runs for the
+// longest lane's candidate list, not for the union of all lanes' leaves (ncu on Mesh.json: the
+// leaf-major loop issued 2/3 of its instructions with <= 3 active lanes).  Candidate order per lane
+// is unchanged (leaf order, then list order), so the first-min / last-max tie rules hold.
 __device__ __forceinline__ bool mesh_test(const SceneCommon& c, uint32_t mesh_id, f3 o_rel, f3 d,
                                           float* t0, float* t1, int* i0, int* i1) {
     const DMesh mh = c.mesh[mesh_id];
-    f3 m = rcp_fixed3(d);
-    f3 om = o_rel * m;
+    const f3 m = rcp_fixed3(d);
+    const f3 om = o_rel * m;
+    {   // root AABB, centred on the instance (Mesh::gen_aabb, rt.rs:261-270)
+        const float ax = fabsf(m.x) * mh.half[0], ay = fabsf(m.y) * mh.half[1], az = fabsf(m.z) * mh.half[2];
+        const float tn = fmaxf(fmaxf(-om.x - ax, -om.y - ay), -om.z - az);
+        const float tf = fminf(fminf(-om.x + ax, -om.y + ay), -om.z + az);
+        if (tn > tf || tf < 0.0f) return false;
+    }
     bool any = false;
     float b0 = 0.f, b1 = 0.f;
     int k0 = -1, k1 = -1;
-    for (uint32_t l = 0; l < mh.n_leaf; l++) {
-        const float4 lo = __ldg(&c.leaf[mh.first_leaf + l].lo);
-        const float4 hi = __ldg(&c.leaf[mh.first_leaf + l].hi);
-        float ax = fmaf(lo.x, m.x, -om.x), bx = fmaf(hi.x, m.x, -om.x);
-        float ay = fmaf(lo.y, m.y, -om.y), by = fmaf(hi.y, m.y, -om.y);
-        float az = fmaf(lo.z, m.z, -om.z), bz = fmaf(hi.z, m.z, -om.z);
-        float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-        float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-        if (tn > tf || tf < 0.0f) continue;
-        const uint32_t first = __float_as_uint(lo.w), cnt = __float_as_uint(hi.w);
-        for (uint32_t k = 0; k < cnt; k++) {
+    for (uint32_t base = 0; base < mh.n_leaf; base += 32u) {
+        const uint32_t n = min(32u, mh.n_leaf - base);
+        uint32_t mask = 0u;
+        for (uint32_t l = 0; l < n; l++) {
+            const float4 lo = __ldg(&c.leaf[mh.first_leaf + base + l].lo);
+            const float4 hi = __ldg(&c.leaf[mh.first_leaf + base + l].hi);
+            const float ax = fmaf(lo.x, m.x, -om.x), bx = fmaf(hi.x, m.x, -om.x);
+            const float ay = fmaf(lo.y, m.y, -om.y), by = fmaf(hi.y, m.y, -om.y);
+            const float az = fmaf(lo.z, m.z, -om.z), bz = fmaf(hi.z, m.z, -om.z);
+            const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+            if (!(tn > tf || tf < 0.0f)) mask |= 1u << l;
+        }
+        uint32_t first = 0u, cnt = 0u, k = 0u;
+        for (;;) {
+            if (k == cnt) {  // next pierced leaf of this lane (leaves are never empty)
+                if (mask == 0u) break;
+                const uint32_t l = (uint32_t)__ffs((int)mask) - 1u;
+                mask &= mask - 1u;
+                first = __float_as_uint(__ldg(&c.leaf[mh.first_leaf + base + l].lo.w));
+                cnt = __float_as_uint(__ldg(&c.leaf[mh.first_leaf + base + l].hi.w));
+                k = 0u;
+            }
             const uint32_t ti = __ldg(&c.leaf_idx[first + k]);
+            k++;
             const DTri* tp = &c.tri[mh.first_tri + ti];
             DTri tr;
             tr.v0 = __ldg(&tp->v0); tr.e0 = __ldg(&tp->e0); tr.e1 = __ldg(&tp->e1);

@@ -26,7 +26,7 @@ CASES = [
 @pytest.fixture(scope="module", params=["generic", "jit"])
 def pair(request):
     """Every parity test runs twice: through the offline-compiled generic kernels and through the
-    run-time scene-specialised kernel (MRT_OPT_JIT; scenes of more than 64 primitives stay generic)."""
+    run-time scene-specialised kernel (MRT_OPT_JIT; scenes of more than 128 primitives stay generic)."""
     from micro_raytracer_b200.sampler import JIT_FORCE, JIT_OFF, OPT_JIT
     gpu = mrt.Sampler(device=0)
     gpu.set_option(OPT_JIT, JIT_FORCE if request.param == "jit" else JIT_OFF)
@@ -86,7 +86,7 @@ def test_shared_rng_paths_match_oracle(pair, name, res, ssaa):
     assert np.isfinite(ag).all()
     st = gpu.jit_status()
     assert st["compiled"] == (gpu.jit_expected and st["eligible"]), st
-    if name in ("CornellBox2", "CornellBox", "dof", "Default", "Mesh"):
+    if name != "Instance":
         assert st["eligible"]
     ok = np.abs(ag - ac).max(axis=2) <= 1e-3 + 2e-3 * np.abs(ac).max(axis=2)
     assert ok.mean() >= 0.95, f"{name}: only {ok.mean():.4%} pixels match"
@@ -251,7 +251,9 @@ def test_jit_auto_compiles_in_the_background_and_switches_over(tmp_path, monkeyp
     from micro_raytracer_b200.sampler import JIT_AUTO, JIT_OFF, OPT_JIT
     monkeypatch.setenv("MRT_JIT_CACHE", str(tmp_path))  # a cold on-disk cache
     r = load("CornellBox", (96, 54), 1.0)
-    r.scene.renderer[0].mat.albedo = (0.7311, 0.7312, 0.7313)  # a scene no other test compiled in this process
+    for o in r.scene.renderer:  # geometry no other test compiled in this process (the cache key is the geometry)
+        if o.kind == "sphere":
+            o.r *= 1.0 + 1e-4
     a, b = mrt.Sampler(device=0), mrt.Sampler(device=0)
     a.set_option(OPT_JIT, JIT_AUTO)
     b.set_option(OPT_JIT, JIT_OFF)

@@ -22,8 +22,11 @@ CONFIGS = [
 
 def main():
     cpu = "--cpu" in sys.argv
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     rows = []
     for label, name, res, ssaa, rt, passes in CONFIGS:
+        if only and name != only:
+            continue
         r = load(name, res, ssaa, **rt)
         s = mrt.Sampler(device=0)
         s.execute(r.scene, r.frame, r.rt, 1)  # upload + warm-up (+ JIT compile when eligible: needs a big call)
