@@ -68,3 +68,32 @@ def test_scene_loader_defaults_match_parser_rs():
     r = load("Minecraft")
     p = mrt.pack_scene(r.scene)
     assert p.c.n_instances == 85 and p.c.n_textures >= 9
+
+
+def test_header_is_valid_c_and_links_from_c(tmp_path):
+    """include/mrt.h is a C header (the Rust/cgo/ctypes side binds it as C): a C translation unit
+    including it compiles with gcc and links against libmrt.so; without a GPU mrt_create must fail
+    with MRT_ERR_CUDA and a message, never abort."""
+    import subprocess
+    src = tmp_path / "abi_c.c"
+    src.write_text('''
+#include <stdio.h>
+#include "mrt.h"
+int main(void) {
+    mrt_ctx* ctx = NULL;
+    mrt_scene sc; mrt_frame fr; mrt_hit h; mrt_material m;
+    (void)sc; (void)fr; (void)h; (void)m;
+    if (mrt_abi_version() != MRT_ABI_VERSION) return 10;
+    int rc = mrt_create(&ctx, 0, 24, 64);
+    if (rc == MRT_OK) { mrt_destroy(ctx); printf("created\\n"); return 0; }
+    printf("rc=%d msg=%s\\n", rc, mrt_last_error(NULL));
+    return rc == MRT_ERR_CUDA ? 0 : 11;
+}
+''')
+    exe = tmp_path / "abi_c"
+    libdir = os.path.dirname(mrt.lib_path())
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:libmrt.so", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "created" in out.stdout or "no CUDA device" in out.stdout or "CUDA" in out.stdout
