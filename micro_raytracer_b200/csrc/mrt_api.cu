@@ -98,6 +98,8 @@ struct mrt_ctx {
     DevBuf<SlimInst> d_slim[K_NKIND];
     DevBuf<Xf> d_mesh_m;
     DevBuf<BoxPair> d_boxp;
+    DevBuf<BvhNode> d_bvh;
+    DevBuf<uint32_t> d_bvh_ref;
     DevBuf<BxfInst> d_bxf;
     DevBuf<FatInst> d_fat;
     DevBuf<DTex> d_tex;
@@ -233,6 +235,52 @@ bool all_finite(const float* v, int n) {
     return true;
 }
 
+// ---- scene-level BVH over the finite instances (mrt_device.cuh: BvhNode): median split of the
+// centroids along the widest axis, <= 4 references per leaf, children adjacent.
+struct PrimBox { float lo[3], hi[3]; uint32_t ref; };
+void bvh_build(std::vector<PrimBox>& prims, size_t begin, size_t end, size_t node, std::vector<BvhNode>* nodes, std::vector<uint32_t>* refs) {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (size_t i = begin; i < end; i++)
+        for (int a = 0; a < 3; a++) {
+            lo[a] = std::fmin(lo[a], prims[i].lo[a]); hi[a] = std::fmax(hi[a], prims[i].hi[a]);
+            const float cc = 0.5f * (prims[i].lo[a] + prims[i].hi[a]);
+            clo[a] = std::fmin(clo[a], cc); chi[a] = std::fmax(chi[a], cc);
+        }
+    if (end - begin <= 4) {
+        (*nodes)[node].lo = make_float4(lo[0], lo[1], lo[2], u2f((uint32_t)refs->size()));
+        (*nodes)[node].hi = make_float4(hi[0], hi[1], hi[2], u2f((uint32_t)(end - begin)));
+        for (size_t i = begin; i < end; i++) refs->push_back(prims[i].ref);
+        return;
+    }
+    int ax = 0;
+    if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
+    if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
+    const size_t mid = begin + (end - begin) / 2;
+    std::nth_element(prims.begin() + begin, prims.begin() + mid, prims.begin() + end, [ax](const PrimBox& a, const PrimBox& b) {
+        return a.lo[ax] + a.hi[ax] < b.lo[ax] + b.hi[ax];
+    });
+    const size_t left = nodes->size();
+    nodes->resize(left + 2);
+    (*nodes)[node].lo = make_float4(lo[0], lo[1], lo[2], u2f((uint32_t)left));
+    (*nodes)[node].hi = make_float4(hi[0], hi[1], hi[2], u2f(0u));
+    bvh_build(prims, begin, mid, left, nodes, refs);
+    bvh_build(prims, mid, end, left + 1, nodes, refs);
+}
+// world-space AABB of an object-space box of half extents h centred on pos, under world->object matrix M
+// (object->world is M^T), padded so that rounding in the primitive tests cannot leave the node
+void world_box(const HM& M, H3 pos, H3 h, PrimBox* b) {
+    const float hw[3] = {std::fabs(M.m[0]) * h.x + std::fabs(M.m[3]) * h.y + std::fabs(M.m[6]) * h.z,
+                         std::fabs(M.m[1]) * h.x + std::fabs(M.m[4]) * h.y + std::fabs(M.m[7]) * h.z,
+                         std::fabs(M.m[2]) * h.x + std::fabs(M.m[5]) * h.y + std::fabs(M.m[8]) * h.z};
+    const float p[3] = {pos.x, pos.y, pos.z};
+    for (int a = 0; a < 3; a++) {
+        const float pad = 1e-4f * (std::fabs(hw[a]) + std::fabs(p[a])) + 1e-5f;
+        b->lo[a] = p[a] - std::fabs(hw[a]) - pad;
+        b->hi[a] = p[a] + std::fabs(hw[a]) + pad;
+    }
+}
+
 uint32_t pack_ids(int32_t lo, int32_t hi) { return ((uint32_t)(lo < 0 ? 0xffff : lo) & 0xffffu) | (((uint32_t)(hi < 0 ? 0xffff : hi) & 0xffffu) << 16); }
 
 }  // namespace
@@ -284,7 +332,7 @@ void mrt_destroy(mrt_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->jit_requested && !c->jit_header.empty()) mrt_jit_wait(c->jit_header);
     for (auto& b : c->d_slim) b.release();
-    c->d_boxp.release(); c->d_bxf.release(); c->d_mesh_m.release(); c->d_fat.release(); c->d_tex.release(); c->d_texels.release();
+    c->d_boxp.release(); c->d_bvh.release(); c->d_bvh_ref.release(); c->d_bxf.release(); c->d_mesh_m.release(); c->d_fat.release(); c->d_tex.release(); c->d_texels.release();
     c->d_mesh.release(); c->d_leaf.release(); c->d_leaf_idx.release(); c->d_tri.release(); c->d_obj_inst.release();
     c->d_accum.release(); c->d_ss.release(); c->d_out.release(); c->d_tmp.release(); c->d_rgb.release();
     c->d_wv.release(); c->d_wh.release(); c->d_lv.release(); c->d_cv.release(); c->d_lh.release(); c->d_ch.release();
@@ -365,6 +413,8 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     std::vector<uint32_t> oi_k[K_NKIND];
     std::vector<Xf> mesh_m;
     std::vector<BxfInst> bxf;
+    std::vector<PrimBox> prim_boxes;  // finite instances, for the scene-level BVH
+    bool prim_boxes_ok = true;
     for (uint32_t oi = 0; oi < s->n_objects; oi++) {
         const mrt_object& o = s->objects[oi];
         const mrt_material& mt = o.mat;
@@ -398,14 +448,18 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
             uint32_t kind;
             Xf x{};
             for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) x.m[4 * r + cc] = M.m[3 * r + cc];
+            PrimBox pb{};
+            bool finite_prim = true;
             if (o.kind == MRT_SPHERE) {
                 kind = K_SPHERE;
                 const float r = o.param[0];
+                world_box(M, pos, {std::fabs(r), std::fabs(r), std::fabs(r)}, &pb);
                 si.a = make_float4(pos.x, pos.y, pos.z, 0.0f);
                 si.b = make_float4(r * r, 0.0f, 0.0f, 0.0f);
                 fi.A = make_float4(1.0f / r, r, 0.0f, 0.0f);
             } else if (o.kind == MRT_PLANE) {
                 kind = K_PLANE;
+                finite_prim = false;
                 const H3 nraw = {o.param[0], o.param[1], o.param[2]};
                 const H3 nh = hnorm(nraw);  // Plane::intersect normalises, rt.rs:404
                 // t = -((o_l - pos).n^)/(d_l.n^) with o_l - pos = M(o - pos), d_l = M d  =>  n_w = M^T n^
@@ -417,6 +471,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
                 fi.A = make_float4(ns.x, ns.y, ns.z, 0.0f);
             } else if (o.kind == MRT_BOX) {
                 kind = ident ? K_BOX : K_BOX_XF;
+                world_box(M, pos, {0.5f * std::fabs(o.param[0]), 0.5f * std::fabs(o.param[1]), 0.5f * std::fabs(o.param[2])}, &pb);
                 si.a = make_float4(pos.x, pos.y, pos.z, 0.0f);
                 if (ident) {
                     si.a.w = 0.5f * o.param[0];
@@ -430,6 +485,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
                 fi.A = make_float4((1.0f / o.param[0]) * 2.0f, (1.0f / o.param[1]) * 2.0f, (1.0f / o.param[2]) * 2.0f, 0.0f);  // rt.rs:416
             } else {
                 kind = K_MESH;
+                world_box(M, pos, {meshes[o.mesh].half[0], meshes[o.mesh].half[1], meshes[o.mesh].half[2]}, &pb);
                 si.a = make_float4(pos.x, pos.y, pos.z, 0.0f);
                 si.b = make_float4(u2f(ident ? 0u : 1u), u2f(o.mesh), 0.0f, 0.0f);
                 mesh_m.push_back(x);
@@ -442,6 +498,11 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
             fi.m2 = make_float4(M.m[6], M.m[7], M.m[8], u2f(pack_ids(mt.omap, mt.emap)));
             fi.C = make_float4(mt.albedo[0], mt.albedo[1], mt.albedo[2], mt.emit);
             fi.R = make_float4(mt.rough, mt.metal, mt.glass, mt.opacity);
+            if (finite_prim) {
+                pb.ref = (kind << 28) | (uint32_t)by_kind[kind].size();
+                for (int a = 0; a < 3; a++) prim_boxes_ok &= std::isfinite(pb.lo[a]) && std::isfinite(pb.hi[a]);
+                prim_boxes.push_back(pb);
+            }
             by_kind[kind].push_back(si);
             fat_k[kind].push_back(fi);
             oi_k[kind].push_back(oi | (k << 16));
@@ -473,6 +534,18 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     for (uint32_t k = 0; k < K_NKIND; k++) CK(c->d_slim[k].upload(by_kind[k]));
     CK(c->d_boxp.upload(boxp));
     CK(c->d_bxf.upload(bxf));
+    // scene-level BVH: only for scenes too large to unroll (the specialised kernel covers <= 128 primitives)
+    std::vector<BvhNode> bvh_nodes;
+    std::vector<uint32_t> bvh_refs;
+    size_t bvh_min = 128;  // the specialised (unrolled) kernel covers up to 128 primitives
+    if (const char* e = std::getenv("MRT_BVH_MIN")) bvh_min = (size_t)std::max(0, std::atoi(e));  // experiment knob
+    const bool use_bvh = prim_boxes.size() > bvh_min && prim_boxes_ok && prim_boxes.size() < (1u << 28) && !std::getenv("MRT_NO_BVH");
+    if (use_bvh) {
+        bvh_nodes.resize(1);
+        bvh_build(prim_boxes, 0, prim_boxes.size(), 0, &bvh_nodes, &bvh_refs);
+    }
+    CK(c->d_bvh.upload(bvh_nodes));
+    CK(c->d_bvh_ref.upload(bvh_refs));
     CK(c->d_mesh_m.upload(mesh_m));
     CK(c->d_fat.upload(fat));
     CK(c->d_tex.upload(tex));
@@ -541,9 +614,11 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     c->gscene.c = sc;
     c->gscene.boxp = c->d_boxp.p; c->gscene.sph = c->d_slim[K_SPHERE].p; c->gscene.pln = c->d_slim[K_PLANE].p;
     c->gscene.bxf = c->d_bxf.p;
+    c->gscene.bvh = use_bvh ? c->d_bvh.p : nullptr;
+    c->gscene.bvh_ref = c->d_bvh_ref.p;
     c->gscene.mesh = c->d_slim[K_MESH].p; c->gscene.mesh_m = c->d_mesh_m.p;
     c->in_param = cnt[K_BOX] <= MRT_PB && cnt[K_SPHERE] <= MRT_PS && cnt[K_PLANE] <= MRT_PP && cnt[K_BOX_XF] <= MRT_PX &&
-                  cnt[K_MESH] <= MRT_PM && !std::getenv("MRT_FORCE_GLOBAL_SCENE");
+                  cnt[K_MESH] <= MRT_PM && !use_bvh && !std::getenv("MRT_FORCE_GLOBAL_SCENE");
     if (c->in_param) {
         ParamScene& ps = *c->pscene;
         ps.c = sc;

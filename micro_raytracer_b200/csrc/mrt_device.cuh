@@ -65,6 +65,11 @@ struct FatInst {
 };
 static_assert(sizeof(FatInst) == 128, "FatInst must be one cache line");
 
+// Scene-level BVH over the FINITE instances (everything but planes) of scenes too large to unroll
+// (> 128 primitives).  It only narrows the candidate set: every candidate runs the same
+// primitive test as the brute-force loop and the winner is the lexicographic minimum of (t0, instance
+// index), i.e. exactly the brute-force result.  Children of an inner node are adjacent.
+struct BvhNode { float4 lo, hi; };  // lo.w = bits: left child (inner) / first ref (leaf); hi.w = bits: 0 (inner) / ref count (leaf)
 struct DLight { float4 v_kind; float4 color_pwr; };  // v.xyz (pos or unit -dir), w = kind bits ; color.rgb, pwr
 struct DTex { uint32_t w, h, first, has_dat; };      // texel offset into the float4 texel array
 struct DMeshLeaf { float4 lo, hi; };                  // leaf box relative to instance pos; lo.w = first index (bits), hi.w = count (bits)
@@ -112,6 +117,8 @@ struct GlobalScene {
     const BxfInst* bxf;
     const SlimInst* mesh;
     const Xf* mesh_m;
+    const BvhNode* bvh;        // nullptr: brute force
+    const uint32_t* bvh_ref;   // leaf entries: kind << 28 | index within the kind's table
 };
 
 struct FilmParams {
@@ -209,6 +216,7 @@ __device__ __forceinline__ float2 rng_cam(uint32_t seed, uint32_t sample) {
 struct ParamView {
     static constexpr bool kParam = true;
     static constexpr bool kJit = false;
+    static constexpr bool kBvh = false;
     const ParamScene& s;
     __device__ __forceinline__ const SceneCommon& c() const { return s.c; }
     __device__ __forceinline__ BoxPair boxp(uint32_t k) const { return s.boxp[k]; }
@@ -222,6 +230,7 @@ __device__ __forceinline__ SlimInst ldg_slim(const SlimInst* p) { return {__ldg(
 struct GlobalView {
     static constexpr bool kParam = false;
     static constexpr bool kJit = false;
+    static constexpr bool kBvh = true;
     const GlobalScene& s;
     __device__ __forceinline__ const SceneCommon& c() const { return s.c; }
     __device__ __forceinline__ BoxPair boxp(uint32_t k) const { return {__ldg(&s.boxp[k].q0), __ldg(&s.boxp[k].q1), __ldg(&s.boxp[k].q2)}; }
@@ -238,6 +247,7 @@ struct GlobalView {
 struct JitView {
     static constexpr bool kParam = true;
     static constexpr bool kJit = true;
+    static constexpr bool kBvh = false;
     const SceneCommon& s;
     __device__ __forceinline__ const SceneCommon& c() const { return s; }
 };
@@ -469,6 +479,100 @@ __device__ __forceinline__ void test_mesh(Best& B, const SceneCommon& c, const R
     best_update<F, ANY, WANT_T1, LE>(B, hit, t0, t1, idx, tr0, tr1);
 }
 
+// ---- scene-level BVH (GlobalView only).  LEX = true makes every update lexicographic in
+// (t0, instance index), because the BVH visits candidates in no particular order.
+template <uint32_t F, bool ANY, bool WANT_T1>
+__device__ __forceinline__ void best_update_lex(Best& B, bool hit, float t0, float t1, int idx, int tr0, int tr1) {
+    if constexpr (ANY) {
+        B.any |= hit;
+    } else {
+        if (hit && (t0 < B.t0 || (t0 == B.t0 && idx < B.bi))) {
+            B.t0 = t0; B.bi = idx;
+            if constexpr (WANT_T1) B.t1 = t1;
+            if constexpr ((F & F_MESH) != 0) { B.tr0 = tr0; B.tr1 = tr1; }
+        }
+    }
+}
+// slab interval of an AABB in the ray's parameter, same arithmetic as the primitive box test
+__device__ __forceinline__ bool node_hit(const RayPre& r, float4 lo, float4 hi, float best, float* tn_out) {
+    const float ax = fmaf(lo.x, r.m.x, r.nom.x), bx = fmaf(hi.x, r.m.x, r.nom.x);
+    const float ay = fmaf(lo.y, r.m.y, r.nom.y), by = fmaf(hi.y, r.m.y, r.nom.y);
+    const float az = fmaf(lo.z, r.m.z, r.nom.z), bz = fmaf(hi.z, r.m.z, r.nom.z);
+    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    *tn_out = tn;
+    return tn <= tf && tf >= 0.0f && tn <= best;  // '<=': an equal t0 with a lower index must still be found
+}
+template <uint32_t F, bool ANY, bool WANT_T1>
+__device__ __forceinline__ void bvh_leaf(Best& B, const GlobalScene& s, const RayPre& r, const RayPk& rp, uint32_t ref) {
+    const SceneCommon& c = s.c;
+    const uint32_t kind = ref >> 28, k = ref & 0x0fffffffu;
+    float t0 = 0.f, t1 = 0.f;
+    int tr0 = -1, tr1 = -1;
+    bool hit;
+    if (kind == K_BOX) {  // one lane of a BoxPair, scalar form of test_box_pair
+        const float* q = reinterpret_cast<const float*>(s.boxp + (k >> 1)) + (k & 1u);
+        const float cx = fmaf(__ldg(q + 0), r.m.x, r.nom.x), cy = fmaf(__ldg(q + 2), r.m.y, r.nom.y), cz = fmaf(__ldg(q + 4), r.m.z, r.nom.z);
+        const float hx = __ldg(q + 6), hy = __ldg(q + 8), hz = __ldg(q + 10);
+        t0 = fmaxf(fmaxf(fmaf(hx, r.nam.x, cx), fmaf(hy, r.nam.y, cy)), fmaf(hz, r.nam.z, cz));
+        t1 = fminf(fminf(fmaf(hx, r.am.x, cx), fmaf(hy, r.am.y, cy)), fmaf(hz, r.am.z, cz));
+        hit = fmaxf(t0, 0.0f) <= t1 && t0 < t1;  // as best_update_slab: t0 == t1 (edge graze) is a miss
+        best_update_lex<F, ANY, WANT_T1>(B, hit, t0, t1, (int)k, -1, -1);
+    } else if (kind == K_SPHERE) {
+        const SlimInst e = ldg_slim(s.sph + k);
+        const f3 oc = r.o - xyz(e.a);
+        const float hb = dot(oc, r.d);
+        const float cc = fmaf(oc.z, oc.z, fmaf(oc.y, oc.y, fmaf(oc.x, oc.x, -e.b.x)));
+        const float disc = fmaf(hb, hb, -cc);
+        const float sq = sqrtf(fmaxf(disc, 0.0f));
+        t0 = -hb - sq;
+        best_update_lex<F, ANY, WANT_T1>(B, (disc >= 0.0f) && (t0 >= 0.0f), t0, sq - hb, (int)(c.first[K_SPHERE] + k), -1, -1);
+    } else if (kind == K_BOX_XF) {
+        Best L; L.t0 = __int_as_float(0x7f800000); L.t1 = 0.f; L.bi = -1; L.tr0 = L.tr1 = -1; L.any = false;
+        test_bxf<F, false, true, false>(L, rp, {__ldg(&s.bxf[k].r0), __ldg(&s.bxf[k].r1), __ldg(&s.bxf[k].r2), __ldg(&s.bxf[k].h)}, 0);
+        best_update_lex<F, ANY, WANT_T1>(B, L.bi == 0, L.t0, L.t1, (int)(c.first[K_BOX_XF] + k), -1, -1);
+    } else {
+        if constexpr ((F & F_MESH) != 0) {
+            const SlimInst e = ldg_slim(s.mesh + k);
+            f3 ol = r.o - xyz(e.a), dl = r.d;
+            if (__float_as_uint(e.b.x) != 0u) { ol = mulXf(s.mesh_m[k], ol); dl = mulXf(s.mesh_m[k], r.d); }
+            hit = mesh_test(c, __float_as_uint(e.b.y), ol, dl, &t0, &t1, &tr0, &tr1);
+            best_update_lex<F, ANY, WANT_T1>(B, hit, t0, t1, (int)(c.first[K_MESH] + k), tr0, tr1);
+        }
+    }
+}
+template <uint32_t F, bool ANY, bool WANT_T1>
+__device__ __forceinline__ void bvh_traverse(Best& B, const GlobalScene& s, const RayPre& r, const RayPk& rp) {
+    uint32_t stack[32];
+    int sp = 0;
+    uint32_t node = 0;
+    {
+        float tn;
+        if (!node_hit(r, __ldg(&s.bvh[0].lo), __ldg(&s.bvh[0].hi), B.t0, &tn)) return;
+    }
+    for (;;) {
+        const float4 lo = __ldg(&s.bvh[node].lo), hi = __ldg(&s.bvh[node].hi);
+        const uint32_t cnt = __float_as_uint(hi.w), first = __float_as_uint(lo.w);
+        if (cnt != 0u) {
+            for (uint32_t i = 0; i < cnt; i++) bvh_leaf<F, ANY, WANT_T1>(B, s, r, rp, __ldg(&s.bvh_ref[first + i]));
+            if constexpr (ANY) { if (B.any) return; }
+        } else {
+            float tl, tr;
+            const bool hl = node_hit(r, __ldg(&s.bvh[first].lo), __ldg(&s.bvh[first].hi), B.t0, &tl);
+            const bool hr = node_hit(r, __ldg(&s.bvh[first + 1u].lo), __ldg(&s.bvh[first + 1u].hi), B.t0, &tr);
+            if (hl && hr) {
+                const bool left_first = tl <= tr;
+                if (sp < 32) stack[sp++] = left_first ? first + 1u : first;
+                node = left_first ? first : first + 1u;
+                continue;
+            }
+            if (hl || hr) { node = hl ? first : first + 1u; continue; }
+        }
+        if (sp == 0) return;
+        node = stack[--sp];
+    }
+}
+
 // Duff's device over one kind: ENTRY(k, LE) tests entry k of the kind.
 #define MRT_DUFF(n_expr, ENTRY)                                                  \
     {                                                                            \
@@ -535,6 +639,19 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
 #define E_PLN(k, LE) test_plane<F, ANY, WANT_T1, LE>(B, r, sc.pln(k), (int)(c.first[K_PLANE] + (k)));
 #define E_BXF(k, LE) test_bxf<F, ANY, WANT_T1, LE>(B, rp, sc.bxf(k), (int)(c.first[K_BOX_XF] + (k)));
 #define E_MSH(k, LE) test_mesh<F, ANY, WANT_T1, LE>(B, c, r, sc.mesh(k), sc.mesh_m(k), (int)(c.first[K_MESH] + (k)));
+    if constexpr (V::kBvh) {
+        if (sc.s.bvh != nullptr) {  // warp-uniform: large scenes only
+            bvh_traverse<F, ANY, WANT_T1>(B, sc.s, r, rp);
+            for (uint32_t k = 0; k < c.cnt[K_PLANE]; k++) {  // planes are infinite: brute force, same tie rule
+                const SlimInst e = sc.pln(k);
+                const float t0 = (e.b.x - dot(r.o, xyz(e.a))) * frcp(dot(r.d, xyz(e.a)));
+                best_update_lex<F, ANY, WANT_T1>(B, t0 > 0.0f, t0, t0, (int)(c.first[K_PLANE] + k), -1, -1);
+            }
+            if constexpr (ANY) return B.any;
+            out->t0 = B.t0; out->t1 = B.t1; out->inst = B.bi; out->tri0 = B.tr0; out->tri1 = B.tr1;
+            return B.bi >= 0;
+        }
+    }
     if constexpr (!V::kJit) {
         MRT_DUFF((c.cnt[K_BOX] + 1u) >> 1, E_BOX)
         MRT_DUFF(c.cnt[K_SPHERE], E_SPH)

@@ -45,11 +45,14 @@ def _mesh(rng, n):
     return (c + rng.uniform(-0.15, 0.15, size=(n, 3, 3))).round(4).tolist()
 
 
-def random_scene(seed, res=(56, 40)):
-    rng = np.random.default_rng(seed)
+def random_scene(seed, res=(56, 40), many=False):
+    """many=True: a few objects with 40..160 instances each (> 128 primitives: the scene-level BVH)."""
+    rng = np.random.default_rng(seed + (100000 if many else 0))
     objs = []
-    for _ in range(int(rng.integers(2, 9))):
+    for oi in range(int(rng.integers(2, 9)) if not many else int(rng.integers(2, 5))):
         kind = rng.choice(["sphere", "box", "plane", "mesh"], p=[0.35, 0.4, 0.15, 0.1])
+        if many and oi == 0:
+            kind = rng.choice(["sphere", "box"])
         o = {"type": str(kind)}
         if kind == "sphere":
             o["r"] = float(rng.uniform(0.1, 0.5))
@@ -65,7 +68,15 @@ def random_scene(seed, res=(56, 40)):
         pos = [float(rng.uniform(-1.2, 1.2)), float(rng.uniform(0.6, 3.0)), float(rng.uniform(-0.8, 0.8))]
         if kind == "plane":
             pos = [0.0, 0.0, float(rng.uniform(-1.2, -0.6))]
-        if rng.random() < 0.25 and kind != "plane":
+        if many and kind != "plane":
+            if kind == "sphere":
+                o["r"] *= 0.4
+            elif kind == "box":
+                o["sizes"] = [v * 0.4 for v in o["sizes"]]
+            n_inst = (int(rng.integers(140, 201)) if oi == 0 else int(rng.integers(40, 161))) if kind != "mesh" else int(rng.integers(2, 6))
+            o["inst"] = [[[float(rng.uniform(-2.5, 2.5)), float(rng.uniform(0.5, 6.0)), float(rng.uniform(-1.5, 1.5))],
+                          _dir(rng) if rng.random() < 0.4 else [0, 0, -1, 0]] for _ in range(n_inst)]
+        elif rng.random() < 0.25 and kind != "plane":
             o["inst"] = [[[float(pos[0] + rng.uniform(-1, 1)), float(pos[1] + rng.uniform(0, 1)), float(pos[2] + rng.uniform(-.5, .5))], _dir(rng)]
                          for _ in range(int(rng.integers(1, 4)))]
             if rng.random() < 0.5:
