@@ -415,11 +415,18 @@ struct RayPre { f3 o, d, m, nom, am, nam; };  // m = 1/d (Box::intersect's fix-u
 // Box::intersect, rt.rs:299-333, centre/half form: n = (o - pos) m, k = half |m|,
 // t0 = max(-n - k), t1 = min(-n + k); miss iff t0 > t1 or t1 < 0.  Two boxes per call, one in
 // each f32x2 lane: 9 FFMA2 + 4 FMNMX3 for the pair.  idx = index of box A (B = idx + 1).
-template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
+// c * m + n for a pair of centre coordinates; FOLD (specialised kernel: the operands are literals)
+// drops the multiply when both are zero — the compiler may not (0 * inf), the scene guarantees it.
+template <bool FOLD>
+__device__ __forceinline__ f2 centre_term(float ca, float cb, float m, float n) {
+    if constexpr (FOLD) { if (ca == 0.0f && cb == 0.0f) return bc2(n); }
+    return fma2(pk2(ca, cb), bc2(m), bc2(n));
+}
+template <uint32_t F, bool ANY, bool WANT_T1, bool LE, bool FOLD = false>
 __device__ __forceinline__ void test_box_pair(Best& B, const RayPre& r, const BoxPair e, int idx) {
-    const f2 cx = fma2(pk2(e.q0.x, e.q0.y), bc2(r.m.x), bc2(r.nom.x));
-    const f2 cy = fma2(pk2(e.q0.z, e.q0.w), bc2(r.m.y), bc2(r.nom.y));
-    const f2 cz = fma2(pk2(e.q1.x, e.q1.y), bc2(r.m.z), bc2(r.nom.z));
+    const f2 cx = centre_term<FOLD>(e.q0.x, e.q0.y, r.m.x, r.nom.x);
+    const f2 cy = centre_term<FOLD>(e.q0.z, e.q0.w, r.m.y, r.nom.y);
+    const f2 cz = centre_term<FOLD>(e.q1.x, e.q1.y, r.m.z, r.nom.z);
     const f2 hx = pk2(e.q1.z, e.q1.w), hy = pk2(e.q2.x, e.q2.y), hz = pk2(e.q2.z, e.q2.w);
     float lxa, lxb, lya, lyb, lza, lzb, hxa, hxb, hya, hyb, hza, hzb;
     up2(fma2(hx, bc2(r.nam.x), cx), lxa, lxb); up2(fma2(hx, bc2(r.am.x), cx), hxa, hxb);
@@ -456,12 +463,18 @@ __device__ __forceinline__ void test_plane(Best& B, const RayPre& r, const SlimI
 // direction ride in the two f32x2 lanes: (o_l - pos, d_l)_i = M_i0 (o.x, d.x) + M_i1 (o.y, d.y)
 // + M_i2 (o.z, d.z) + (-(M pos)_i, 0): 9 FFMA2 for both transforms.
 struct RayPk { f2 x, y, z; };  // (o.x, d.x), (o.y, d.y), (o.z, d.z)
-template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
+// acc + c * p; FOLD drops terms whose (literal) matrix entry is zero, e.g. the z row/column of a yaw-only instance
+template <bool FOLD>
+__device__ __forceinline__ f2 row_term(float c, f2 p, f2 acc) {
+    if constexpr (FOLD) { if (c == 0.0f) return acc; }
+    return fma2(bc2(c), p, acc);
+}
+template <uint32_t F, bool ANY, bool WANT_T1, bool LE, bool FOLD = false>
 __device__ __forceinline__ void test_bxf(Best& B, const RayPk& p, const BxfInst e, int idx) {
     float olx, dlx, oly, dly, olz, dlz;
-    up2(fma2(bc2(e.r0.z), p.z, fma2(bc2(e.r0.y), p.y, fma2(bc2(e.r0.x), p.x, pk2(e.r0.w, 0.0f)))), olx, dlx);
-    up2(fma2(bc2(e.r1.z), p.z, fma2(bc2(e.r1.y), p.y, fma2(bc2(e.r1.x), p.x, pk2(e.r1.w, 0.0f)))), oly, dly);
-    up2(fma2(bc2(e.r2.z), p.z, fma2(bc2(e.r2.y), p.y, fma2(bc2(e.r2.x), p.x, pk2(e.r2.w, 0.0f)))), olz, dlz);
+    up2(row_term<FOLD>(e.r0.z, p.z, row_term<FOLD>(e.r0.y, p.y, row_term<FOLD>(e.r0.x, p.x, pk2(e.r0.w, 0.0f)))), olx, dlx);
+    up2(row_term<FOLD>(e.r1.z, p.z, row_term<FOLD>(e.r1.y, p.y, row_term<FOLD>(e.r1.x, p.x, pk2(e.r1.w, 0.0f)))), oly, dly);
+    up2(row_term<FOLD>(e.r2.z, p.z, row_term<FOLD>(e.r2.y, p.y, row_term<FOLD>(e.r2.x, p.x, pk2(e.r2.w, 0.0f)))), olz, dlz);
     const f3 ml = rcp_fixed3(mk(dlx, dly, dlz));
     const float cx = -olx * ml.x, cy = -oly * ml.y, cz = -olz * ml.z;
     const float ax = fabsf(ml.x), ay = fabsf(ml.y), az = fabsf(ml.z);
@@ -609,13 +622,13 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
     if constexpr (V::kJit) {
         // ascending declaration order, strict '<': the first minimum wins (rt.rs:872)
 #define J_BOXP(k, a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11) \
-    test_box_pair<F, ANY, WANT_T1, false>(B, r, BoxPair{make_float4(a0, a1, a2, a3), make_float4(a4, a5, a6, a7), make_float4(a8, a9, a10, a11)}, (int)(2 * (k)));
+    test_box_pair<F, ANY, WANT_T1, false, true>(B, r, BoxPair{make_float4(a0, a1, a2, a3), make_float4(a4, a5, a6, a7), make_float4(a8, a9, a10, a11)}, (int)(2 * (k)));
 #define J_SPH(k, cx, cy, cz, r2) \
     test_sphere<F, ANY, WANT_T1, false>(B, r, SlimInst{make_float4(cx, cy, cz, 0.0f), make_float4(r2, 0.0f, 0.0f, 0.0f)}, (int)(MRT_JIT_FIRST_SPHERE + (k)));
 #define J_PLN(k, nx, ny, nz, off) \
     test_plane<F, ANY, WANT_T1, false>(B, r, SlimInst{make_float4(nx, ny, nz, 0.0f), make_float4(off, 0.0f, 0.0f, 0.0f)}, (int)(MRT_JIT_FIRST_PLANE + (k)));
 #define J_BXF(k, a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, hx, hy, hz) \
-    test_bxf<F, ANY, WANT_T1, false>(B, rp, BxfInst{make_float4(a0, a1, a2, a3), make_float4(a4, a5, a6, a7), make_float4(a8, a9, a10, a11), make_float4(hx, hy, hz, 0.0f)}, (int)(MRT_JIT_FIRST_BXF + (k)));
+    test_bxf<F, ANY, WANT_T1, false, true>(B, rp, BxfInst{make_float4(a0, a1, a2, a3), make_float4(a4, a5, a6, a7), make_float4(a8, a9, a10, a11), make_float4(hx, hy, hz, 0.0f)}, (int)(MRT_JIT_FIRST_BXF + (k)));
 #define J_MSH(k, px, py, pz, rot, mid, m0, m1, m2, m3, m4, m5, m6, m7, m8, m9, m10, m11) \
     if constexpr ((F & F_MESH) != 0) { const Xf x__ = {{m0, m1, m2, m3, m4, m5, m6, m7, m8, m9, m10, m11}}; \
         test_mesh<F, ANY, WANT_T1, false>(B, c, r, SlimInst{make_float4(px, py, pz, 0.0f), make_float4(__uint_as_float(rot), __uint_as_float(mid), 0.0f, 0.0f)}, x__, (int)(MRT_JIT_FIRST_MESH + (k))); }
