@@ -591,7 +591,10 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
             lits(&h, mesh_m[k].m, 12); });
         // big unrolled scenes: without a register budget ptxas hoists every operand (254 registers, 2 blocks
         // per SM on Minecraft.json); 3 blocks (168 registers) measured best there: 2594 -> 2757 Mpaths/s
-        if (n_prim > 48 && !std::getenv("MRT_JIT_MINBLOCKS")) h += "#define MRT_JIT_MINBLOCKS 3\n";
+        if (n_prim > 48 && !(std::getenv("MRT_JIT_MINBLOCKS") && *std::getenv("MRT_JIT_MINBLOCKS"))) h += "#define MRT_JIT_MINBLOCKS 3\n";
+        h += "#define MRT_JIT_N_BOX " + std::to_string(cnt[K_BOX] + cnt[K_BOX_XF]) + "\n";
+        h += "#define MRT_JIT_N_SPHERE " + std::to_string(cnt[K_SPHERE]) + "\n";
+        h += "#define MRT_JIT_N_PLANE " + std::to_string(cnt[K_PLANE]) + "\n";
         h += "#define MRT_JIT_FIRST_SPHERE " + std::to_string(first[K_SPHERE]) + "\n";
         h += "#define MRT_JIT_FIRST_PLANE " + std::to_string(first[K_PLANE]) + "\n";
         h += "#define MRT_JIT_FIRST_BXF " + std::to_string(first[K_BOX_XF]) + "\n";

@@ -470,12 +470,17 @@ __device__ __forceinline__ f2 row_term(float c, f2 p, f2 acc) {
     return fma2(bc2(c), p, acc);
 }
 template <uint32_t F, bool ANY, bool WANT_T1, bool LE, bool FOLD = false>
-__device__ __forceinline__ void test_bxf(Best& B, const RayPk& p, const BxfInst e, int idx) {
+__device__ __forceinline__ void test_bxf(Best& B, const RayPk& p, const BxfInst e, int idx, float mz = 0.0f /* the ray's 1/d.z, FOLD only */) {
     float olx, dlx, oly, dly, olz, dlz;
     up2(row_term<FOLD>(e.r0.z, p.z, row_term<FOLD>(e.r0.y, p.y, row_term<FOLD>(e.r0.x, p.x, pk2(e.r0.w, 0.0f)))), olx, dlx);
     up2(row_term<FOLD>(e.r1.z, p.z, row_term<FOLD>(e.r1.y, p.y, row_term<FOLD>(e.r1.x, p.x, pk2(e.r1.w, 0.0f)))), oly, dly);
-    up2(row_term<FOLD>(e.r2.z, p.z, row_term<FOLD>(e.r2.y, p.y, row_term<FOLD>(e.r2.x, p.x, pk2(e.r2.w, 0.0f)))), olz, dlz);
-    const f3 ml = rcp_fixed3(mk(dlx, dly, dlz));
+    bool z_through = false;  // yaw-only instance: the z row of M is (0, 0, 1), so d_l.z = d.z and 1/d_l.z is the ray's own
+    if constexpr (FOLD) z_through = e.r2.x == 0.0f && e.r2.y == 0.0f && e.r2.z == 1.0f;
+    if (z_through) { float oz, dz; up2(p.z, oz, dz); olz = oz + e.r2.w; dlz = dz; }
+    else up2(row_term<FOLD>(e.r2.z, p.z, row_term<FOLD>(e.r2.y, p.y, row_term<FOLD>(e.r2.x, p.x, pk2(e.r2.w, 0.0f)))), olz, dlz);
+    f3 ml;
+    if (z_through) { ml.x = rcp_fixed(dlx); ml.y = rcp_fixed(dly); ml.z = mz; }
+    else ml = rcp_fixed3(mk(dlx, dly, dlz));
     const float cx = -olx * ml.x, cy = -oly * ml.y, cz = -olz * ml.z;
     const float ax = fabsf(ml.x), ay = fabsf(ml.y), az = fabsf(ml.z);
     const float t0 = fmaxf(fmaxf(fmaf(-e.h.x, ax, cx), fmaf(-e.h.y, ay, cy)), fmaf(-e.h.z, az, cz));
@@ -628,7 +633,7 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
 #define J_PLN(k, nx, ny, nz, off) \
     test_plane<F, ANY, WANT_T1, false>(B, r, SlimInst{make_float4(nx, ny, nz, 0.0f), make_float4(off, 0.0f, 0.0f, 0.0f)}, (int)(MRT_JIT_FIRST_PLANE + (k)));
 #define J_BXF(k, a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, hx, hy, hz) \
-    test_bxf<F, ANY, WANT_T1, false, true>(B, rp, BxfInst{make_float4(a0, a1, a2, a3), make_float4(a4, a5, a6, a7), make_float4(a8, a9, a10, a11), make_float4(hx, hy, hz, 0.0f)}, (int)(MRT_JIT_FIRST_BXF + (k)));
+    test_bxf<F, ANY, WANT_T1, false, true>(B, rp, BxfInst{make_float4(a0, a1, a2, a3), make_float4(a4, a5, a6, a7), make_float4(a8, a9, a10, a11), make_float4(hx, hy, hz, 0.0f)}, (int)(MRT_JIT_FIRST_BXF + (k)), r.m.z);
 #define J_MSH(k, px, py, pz, rot, mid, m0, m1, m2, m3, m4, m5, m6, m7, m8, m9, m10, m11) \
     if constexpr ((F & F_MESH) != 0) { const Xf x__ = {{m0, m1, m2, m3, m4, m5, m6, m7, m8, m9, m10, m11}}; \
         test_mesh<F, ANY, WANT_T1, false>(B, c, r, SlimInst{make_float4(px, py, pz, 0.0f), make_float4(__uint_as_float(rot), __uint_as_float(mid), 0.0f, 0.0f)}, x__, (int)(MRT_JIT_FIRST_MESH + (k))); }
@@ -700,12 +705,15 @@ __device__ __forceinline__ void load_surf(const FatInst* f, Surf* s) {
         s->m0 = __ldg(&f->m0);
         s->m1 = __ldg(&f->m1);
         s->m2 = __ldg(&f->m2);
-    } else {  // never read (every use is behind !identity() / textured()); initialised because ptxas
-              // allocates 8 registers fewer with it (64 vs 72: one more resident block per SM)
+    }
+#ifndef MRT_JIT
+    else {  // never read (every use is behind !identity() / textured()); initialised in the offline build
+            // because ptxas allocates 8 registers fewer with it (64 vs 72: one more resident block per SM)
         s->m0 = make_float4(1.f, 0.f, 0.f, __uint_as_float(0xffffffffu));
         s->m1 = make_float4(0.f, 1.f, 0.f, __uint_as_float(0xffffffffu));
         s->m2 = make_float4(0.f, 0.f, 1.f, __uint_as_float(0xffffffffu));
     }
+#endif
 }
 // object-space hit point minus instance pos: rot_y * (look * (hp - pos)), rt.rs:782
 __device__ __forceinline__ f3 to_local(const Surf& s, f3 hp) {
@@ -733,14 +741,24 @@ __device__ __forceinline__ f3 box_face(f3 p) {
 // Renderer::normal, rt.rs:776-793: kind normal of the object-space hit point, pushed through
 // the FORWARD transform again (rt.rs:792; unless MRT_NORMAL_OBJECT is selected) and normalised.  Unit inputs through an orthonormal M
 // stay unit to 1e-7, so only mesh normals need the rsqrt.
+// The specialised kernel knows which kinds the scene holds (MRT_JIT_HAS_*): absent kinds cost nothing.
+#ifdef MRT_JIT
+#define MRT_HAS_PLANE (MRT_JIT_N_PLANE > 0)
+#define MRT_HAS_SPHERE (MRT_JIT_N_SPHERE > 0)
+#define MRT_HAS_BOX (MRT_JIT_N_BOX > 0)
+#else
+#define MRT_HAS_PLANE true
+#define MRT_HAS_SPHERE true
+#define MRT_HAS_BOX true
+#endif
 template <uint32_t F>
 __device__ __forceinline__ f3 surf_normal(const SceneCommon& c, const Surf& s, f3 pl, int tri) {
     const uint32_t k = s.kind();
-    if (k == K_PLANE) return xyz(s.A);  // precomputed norm(M n)
+    if (MRT_HAS_PLANE && k == K_PLANE) return xyz(s.A);  // precomputed norm(M n)
     f3 n;
     bool mesh = false;
     if constexpr ((F & F_MESH) != 0) mesh = k == K_MESH;
-    if (k == K_SPHERE) n = pl * s.A.x;  // (hit - pos) / r
+    if (MRT_HAS_SPHERE && (k == K_SPHERE || (!MRT_HAS_BOX && !mesh))) n = pl * s.A.x;  // (hit - pos) / r
     else if (mesh) {
         const DTri* tp = &c.tri[__float_as_uint(s.A.x) + (uint32_t)tri];
         n = cross(xyz(__ldg(&tp->e0)), xyz(__ldg(&tp->e1)));  // rt.rs:459-466
