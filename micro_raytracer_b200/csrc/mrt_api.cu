@@ -592,6 +592,22 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
         // big unrolled scenes: without a register budget ptxas hoists every operand (254 registers, 2 blocks
         // per SM on Minecraft.json); 3 blocks (168 registers) measured best there: 2594 -> 2757 Mpaths/s
         if (n_prim > 48 && !(std::getenv("MRT_JIT_MINBLOCKS") && *std::getenv("MRT_JIT_MINBLOCKS"))) h += "#define MRT_JIT_MINBLOCKS 3\n";
+        {   // rough/metal/glass/opacity shared by every material (and no map overrides them): fold them in
+            bool uni = s->n_objects > 0;
+            const mrt_material& m0 = s->objects[0].mat;
+            for (uint32_t oi = 0; oi < s->n_objects && uni; oi++) {
+                const mrt_material& m = s->objects[oi].mat;
+                uni = m.rough == m0.rough && m.metal == m0.metal && m.glass == m0.glass && m.opacity == m0.opacity &&
+                      m.rmap < 0 && m.mmap < 0 && m.gmap < 0 && m.omap < 0;
+            }
+            const float v[4] = {m0.rough, m0.metal, m0.glass, m0.opacity};
+            if (uni && all_finite(v, 4)) {
+                h += "#define MRT_JIT_UNIFORM_R ";
+                std::string t;
+                lits(&t, v, 4);
+                h += t.substr(2) + "\n";
+            }
+        }
         h += "#define MRT_JIT_N_BOX " + std::to_string(cnt[K_BOX] + cnt[K_BOX_XF]) + "\n";
         h += "#define MRT_JIT_N_SPHERE " + std::to_string(cnt[K_SPHERE]) + "\n";
         h += "#define MRT_JIT_N_PLANE " + std::to_string(cnt[K_PLANE]) + "\n";

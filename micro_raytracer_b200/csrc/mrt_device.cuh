@@ -727,12 +727,12 @@ __device__ __forceinline__ f3 to_local(const Surf& s, f3 hp) {
 // vector (NaN normal, measured 1e-7 of hits); the nearest face is taken instead.
 __device__ __forceinline__ f3 box_face(f3 p) {
     // windowed axes get a score that encodes the reference's priority (z over x over y); the rest
-    // score their distance from the face, so the largest score also picks the nearest face when no
-    // window matches.  Branch-free: 3 FADD, 3 FSETP, 3 FSEL, 2 FSETP + PLOP3, 3 LOP3, 3 FSEL.
+    // score e = |p_i| - 1 (<= 0 on the surface), so the largest score also picks the nearest face
+    // when no window matches.  Branch-free.
     const float ex = fabsf(p.x) - 1.0f, ey = fabsf(p.y) - 1.0f, ez = fabsf(p.z) - 1.0f;
-    const float sz = fabsf(ez) < MRT_E ? 3.0f : -fabsf(ez);
-    const float sx = fabsf(ex) < MRT_E ? 2.0f : -fabsf(ex);
-    const float sy = fabsf(ey) < MRT_E ? 1.0f : -fabsf(ey);
+    const float sz = fabsf(ez) < MRT_E ? 3e30f : ez;
+    const float sx = fabsf(ex) < MRT_E ? 2e30f : ex;
+    const float sy = fabsf(ey) < MRT_E ? 1e30f : ey;
     const bool fz = sz >= sx && sz >= sy;
     const bool fx = !fz && sx >= sy;
     const bool fy = !fz && !fx;
@@ -823,7 +823,11 @@ struct Mat {
 template <uint32_t F>
 __device__ __forceinline__ void load_mat(const SceneCommon& c, const FatInst* f, const Surf& s, f3 pl, Mat* m) {
     const float4 ae = __ldg(&f->C);
+#if defined(MRT_JIT) && defined(MRT_JIT_UNIFORM_R)
+    const float4 r = make_float4(MRT_JIT_UNIFORM_R);  // every material of the scene has these rough/metal/glass/opacity: literals
+#else
     const float4 r = __ldg(&f->R);
+#endif
     m->color = xyz(ae); m->emit = ae.w;
     m->rough = r.x; m->metal = r.y; m->glass = r.z; m->opacity = r.w; m->metal_raw = r.y;
     if constexpr ((F & F_TEX) != 0) {
