@@ -429,9 +429,18 @@ __device__ __forceinline__ void test_box_pair(Best& B, const RayPre& r, const Bo
     const f2 cz = centre_term<FOLD>(e.q1.x, e.q1.y, r.m.z, r.nom.z);
     const f2 hx = pk2(e.q1.z, e.q1.w), hy = pk2(e.q2.x, e.q2.y), hz = pk2(e.q2.z, e.q2.w);
     float lxa, lxb, lya, lyb, lza, lzb, hxa, hxb, hya, hyb, hza, hzb;
-    up2(fma2(hx, bc2(r.nam.x), cx), lxa, lxb); up2(fma2(hx, bc2(r.am.x), cx), hxa, hxb);
-    up2(fma2(hy, bc2(r.nam.y), cy), lya, lyb); up2(fma2(hy, bc2(r.am.y), cy), hya, hyb);
-    up2(fma2(hz, bc2(r.nam.z), cz), lza, lzb); up2(fma2(hz, bc2(r.am.z), cz), hza, hzb);
+    if constexpr (FOLD) {  // literal half extents: negate them at compile time instead of -|m| at run time
+        up2(fma2(pk2(-e.q1.z, -e.q1.w), bc2(r.am.x), cx), lxa, lxb);
+        up2(fma2(pk2(-e.q2.x, -e.q2.y), bc2(r.am.y), cy), lya, lyb);
+        up2(fma2(pk2(-e.q2.z, -e.q2.w), bc2(r.am.z), cz), lza, lzb);
+    } else {
+        up2(fma2(hx, bc2(r.nam.x), cx), lxa, lxb);
+        up2(fma2(hy, bc2(r.nam.y), cy), lya, lyb);
+        up2(fma2(hz, bc2(r.nam.z), cz), lza, lzb);
+    }
+    up2(fma2(hx, bc2(r.am.x), cx), hxa, hxb);
+    up2(fma2(hy, bc2(r.am.y), cy), hya, hyb);
+    up2(fma2(hz, bc2(r.am.z), cz), hza, hzb);
     const float t0a = fmaxf(fmaxf(lxa, lya), lza), t1a = fminf(fminf(hxa, hya), hza);
     const float t0b = fmaxf(fmaxf(lxb, lyb), lzb), t1b = fminf(fminf(hxb, hyb), hzb);
     if constexpr (LE) {  // descending traversal: B first, ties go to the lower index
