@@ -571,7 +571,27 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
             for (size_t k = 0; k < n; k++) { h += " X(" + std::to_string(k); row(k); h += ")"; }
             h += "\n";
         };
-        tab("MRT_JIT_BOXPAIRS", boxp.size(), [&](size_t k) { ok &= all_finite(&boxp[k].q0.x, 12); lits(&h, &boxp[k].q0.x, 12); });
+        // box pairs: X = packed FFMA2 pair, XS = the two boxes one at a time, X1 = single box (odd count).
+        // A pair constant whose two lanes differ costs two uniform-register moves per use in the packed form
+        // (only equal lanes are an immediate broadcast), so lopsided pairs are cheaper unpacked.
+        h += "#define MRT_JIT_BOXPAIRS(X, XS, X1)";
+        for (size_t k = 0; k < boxp.size(); k++) {
+            const float* q = &boxp[k].q0.x;  // (cA.x,cB.x, cA.y,cB.y, cA.z,cB.z, hA.x,hB.x, hA.y,hB.y, hA.z,hB.z)
+            ok &= all_finite(q, 12);
+            const bool odd = 2 * k + 1 >= by_kind[K_BOX].size();
+            int packed = 6, scalar = 12;
+            for (int a = 0; a < 3; a++) {
+                const float ca = q[2 * a], cb = q[2 * a + 1], ha = q[6 + 2 * a], hb = q[7 + 2 * a];
+                if (ca != 0.0f || cb != 0.0f) packed += 1 + (ca != cb ? 2 : 0);
+                if (ha != hb) packed += 4;  // +h and -h pairs
+                scalar += (ca != 0.0f) + (cb != 0.0f);
+            }
+            h += odd ? " X1(" : (scalar < packed ? " XS(" : " X(");
+            h += std::to_string(k);
+            lits(&h, q, 12);
+            h += ")";
+        }
+        h += "\n";
         tab("MRT_JIT_SPHERES", by_kind[K_SPHERE].size(), [&](size_t k) {
             const SlimInst& e = by_kind[K_SPHERE][k];
             const float v[4] = {e.a.x, e.a.y, e.a.z, e.b.x};

@@ -451,6 +451,17 @@ __device__ __forceinline__ void test_box_pair(Best& B, const RayPre& r, const Bo
         best_update_slab<F, ANY, WANT_T1, LE>(B, t0b, t1b, idx + 1);
     }
 }
+// One box with literal operands (specialised kernel): used where packing two boxes would cost more
+// uniform-register moves than it saves (lanes of the pair with different constants), and for the odd box.
+template <uint32_t F, bool ANY, bool WANT_T1>
+__device__ __forceinline__ void test_box_lit(Best& B, const RayPre& r, float px, float py, float pz, float hx, float hy, float hz, int idx) {
+    const float cx = px == 0.0f ? r.nom.x : fmaf(px, r.m.x, r.nom.x);
+    const float cy = py == 0.0f ? r.nom.y : fmaf(py, r.m.y, r.nom.y);
+    const float cz = pz == 0.0f ? r.nom.z : fmaf(pz, r.m.z, r.nom.z);
+    const float t0 = fmaxf(fmaxf(fmaf(-hx, r.am.x, cx), fmaf(-hy, r.am.y, cy)), fmaf(-hz, r.am.z, cz));
+    const float t1 = fminf(fminf(fmaf(hx, r.am.x, cx), fmaf(hy, r.am.y, cy)), fmaf(hz, r.am.z, cz));
+    best_update_slab<F, ANY, WANT_T1, false>(B, t0, t1, idx);
+}
 // Sphere::intersect, rt.rs:335-359, with a = d.d = 1 (directions are unit), half-b form
 template <uint32_t F, bool ANY, bool WANT_T1, bool LE>
 __device__ __forceinline__ void test_sphere(Best& B, const RayPre& r, const SlimInst e, int idx) {
@@ -637,6 +648,11 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
         // ascending declaration order, strict '<': the first minimum wins (rt.rs:872)
 #define J_BOXP(k, a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11) \
     test_box_pair<F, ANY, WANT_T1, false, true>(B, r, BoxPair{make_float4(a0, a1, a2, a3), make_float4(a4, a5, a6, a7), make_float4(a8, a9, a10, a11)}, (int)(2 * (k)));
+#define J_BOXS(k, a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11) /* the same pair, one box at a time */ \
+    test_box_lit<F, ANY, WANT_T1>(B, r, a0, a2, a4, a6, a8, a10, (int)(2 * (k))); \
+    test_box_lit<F, ANY, WANT_T1>(B, r, a1, a3, a5, a7, a9, a11, (int)(2 * (k) + 1));
+#define J_BOX1(k, a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11) /* odd box count: lane B is padding */ \
+    test_box_lit<F, ANY, WANT_T1>(B, r, a0, a2, a4, a6, a8, a10, (int)(2 * (k)));
 #define J_SPH(k, cx, cy, cz, r2) \
     test_sphere<F, ANY, WANT_T1, false>(B, r, SlimInst{make_float4(cx, cy, cz, 0.0f), make_float4(r2, 0.0f, 0.0f, 0.0f)}, (int)(MRT_JIT_FIRST_SPHERE + (k)));
 #define J_PLN(k, nx, ny, nz, off) \
@@ -646,12 +662,14 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
 #define J_MSH(k, px, py, pz, rot, mid, m0, m1, m2, m3, m4, m5, m6, m7, m8, m9, m10, m11) \
     if constexpr ((F & F_MESH) != 0) { const Xf x__ = {{m0, m1, m2, m3, m4, m5, m6, m7, m8, m9, m10, m11}}; \
         test_mesh<F, ANY, WANT_T1, false>(B, c, r, SlimInst{make_float4(px, py, pz, 0.0f), make_float4(__uint_as_float(rot), __uint_as_float(mid), 0.0f, 0.0f)}, x__, (int)(MRT_JIT_FIRST_MESH + (k))); }
-        MRT_JIT_BOXPAIRS(J_BOXP)
+        MRT_JIT_BOXPAIRS(J_BOXP, J_BOXS, J_BOX1)
         MRT_JIT_SPHERES(J_SPH)
         MRT_JIT_PLANES(J_PLN)
         MRT_JIT_BXFS(J_BXF)
         MRT_JIT_MESHES(J_MSH)
 #undef J_BOXP
+#undef J_BOXS
+#undef J_BOX1
 #undef J_SPH
 #undef J_PLN
 #undef J_BXF

@@ -4,7 +4,10 @@ import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src = os.path.join(ROOT, "micro_raytracer_b200", "csrc")
 DEFAULT = """
-#define MRT_JIT_BOXPAIRS(X) X(0, 0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p-1f,0x1p-1f,0x1p-1f,0x1p-1f,0x1p-1f,-0x1p+0f)
+#define MRT_JIT_N_BOX 3
+#define MRT_JIT_N_SPHERE 1
+#define MRT_JIT_N_PLANE 1
+#define MRT_JIT_BOXPAIRS(X, XS, X1) XS(1, 0x1p+0f,0x1p+1f,0x0p+0f,0x1p+0f,0x1p+0f,0x0p+0f,0x1p-1f,0x1p-2f,0x1p-1f,0x1p-1f,0x1p-1f,0x1p-3f) X1(2, 0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p-1f,-0x1p+0f,0x1p-1f,-0x1p+0f,0x1p-1f,-0x1p+0f) X(0, 0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p-1f,0x1p-1f,0x1p-1f,0x1p-1f,0x1p-1f,-0x1p+0f)
 #define MRT_JIT_SPHERES(X) X(0, 0x1p+0f, 0x1p+1f, 0x1p+0f, 0x1p-2f)
 #define MRT_JIT_PLANES(X) X(0, 0x0p+0f, 0x0p+0f, 0x1p+0f, -0x1p+0f)
 #define MRT_JIT_BXFS(X) X(0, 0x1p-1f,0x1p-1f,0x0p+0f,0x1p+0f, -0x1p-1f,0x1p-1f,0x0p+0f,0x1p+0f, 0x0p+0f,0x0p+0f,0x1p+0f,0x1p+0f, 0x1p-2f,0x1p-2f,0x1p-2f)
