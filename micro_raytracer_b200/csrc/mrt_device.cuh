@@ -184,7 +184,12 @@ __device__ __forceinline__ f3 rcp_fixed3(f3 d) { return {rcp_fixed(d.x), rcp_fix
 // ------------------------------------------------------------------ RNG: pcg4d counter hash
 // (Jarzynski & Olano, JCGT 2020).  One call = the 4 uniforms of (pixel, sample, block);
 // identical to oracle/mrt_oracle.cpp rng_block so both consume the same numbers.
-__device__ __forceinline__ float4 rng_block(uint32_t pixel, uint32_t sample, uint32_t block, uint32_t key) {
+// The four 32-bit words of a block; a uniform is word * MRT_U32_TO_UNIT in [0, 1 - 2^-24] (the scale
+// is (1 - 2^-24) 2^-32 so that a word that rounds up to 2^32 still maps below 1).
+#define MRT_U32_TO_UNIT 0x1.fffffep-33f
+// u < 0.8f  <=>  word < MRT_LOTTERY_80 (exact: float(word) * MRT_U32_TO_UNIT is monotone in word)
+#define MRT_LOTTERY_80 0xCCCCCD80u
+__device__ __forceinline__ uint4 rng_words(uint32_t pixel, uint32_t sample, uint32_t block, uint32_t key) {
     uint32_t x = pixel * 1664525u + 1013904223u;
     uint32_t y = sample * 1664525u + 1013904223u;
     uint32_t z = block * 1664525u + 1013904223u;
@@ -192,8 +197,11 @@ __device__ __forceinline__ float4 rng_block(uint32_t pixel, uint32_t sample, uin
     x += y * w; y += z * x; z += x * y; w += y * z;
     x ^= x >> 16; y ^= y >> 16; z ^= z >> 16; w ^= w >> 16;
     x += y * w; y += z * x; z += x * y; w += y * z;
-    const float s = 1.0f / 16777216.0f;
-    return make_float4((float)(x >> 8) * s, (float)(y >> 8) * s, (float)(z >> 8) * s, (float)(w >> 8) * s);
+    return make_uint4(x, y, z, w);
+}
+__device__ __forceinline__ float4 rng_block(uint32_t pixel, uint32_t sample, uint32_t block, uint32_t key) {
+    const uint4 v = rng_words(pixel, sample, block, key);
+    return make_float4((float)v.x * MRT_U32_TO_UNIT, (float)v.y * MRT_U32_TO_UNIT, (float)v.z * MRT_U32_TO_UNIT, (float)v.w * MRT_U32_TO_UNIT);
 }
 
 // Camera block: the 2 lens uniforms of (pixel, sample).  The lens jitter only needs a cheap
@@ -880,5 +888,13 @@ __device__ __forceinline__ f3 rand_normal(f3 n, float r, float u1, float u2) {
     __sincosf(u2 * 6.283185307179586f, &sp, &cp);
     f3 v = mk(st * cp, st * sp, z);
     return normalize(fma3(v, r, n));
+}
+// the same from the raw words: the conversions fold into the first multiply of each use
+__device__ __forceinline__ f3 rand_normal_w(f3 n, float r, uint32_t w1, uint32_t w2) {
+    const float z = fmaf((float)w1, -2.0f * MRT_U32_TO_UNIT, 1.0f);
+    const float st = sqrtf(fmaxf(0.0f, fmaf(-z, z, 1.0f)));
+    float sp, cp;
+    __sincosf((float)w2 * (6.283185307179586f * MRT_U32_TO_UNIT), &sp, &cp);
+    return normalize(fma3(mk(st * cp, st * sp, z), r, n));
 }
 __device__ __forceinline__ f3 reflect3(f3 v, f3 n) { return fma3(n, -2.0f * dot(v, n), v); }  // lin.rs:68-70

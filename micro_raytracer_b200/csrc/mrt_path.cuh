@@ -91,14 +91,14 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
                 }
             }
 
-            const float4 u = rng_block(pix, sample, 1u + 2u * bounce, fp.key);
+            const uint4 uw = rng_words(pix, sample, 1u + 2u * bounce, fp.key);  // x: reflect lottery, y z: direction, w: emission draw
 
             // Ray::reflect from the entry hit, rt.rs:559-572
             f3 nd, no;
             {
                 float rough = m.rough;
-                if (m.metal_raw == 0.0f && m.opacity != 0.0f && u.x < 0.80f) rough = 1.0f;
-                const f3 nn = rand_normal(n, rough, u.y, u.z);
+                if (m.metal_raw == 0.0f && m.opacity != 0.0f && uw.x < MRT_LOTTERY_80) rough = 1.0f;  // u < 0.8
+                const f3 nn = rand_normal_w(n, rough, uw.y, uw.z);
                 nd = reflect3(d, nn);  // unit d about unit nn stays unit (the reference's .norm() is a no-op to 1e-7)
                 no = fma3(nd, MRT_E, hp);
             }
@@ -132,7 +132,7 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
             }
 
             // ---- RayTracer::reduce_light, rt.rs:956-994, evaluated forward
-            if (u.w < m.emit) {  // emission draw, rt.rs:966-970
+            if ((float)uw.w * MRT_U32_TO_UNIT < m.emit) {  // emission draw, rt.rs:966-970
                 acc = acc + T * m.color;
                 bounce = 0xffffffffu; j++;
                 continue;

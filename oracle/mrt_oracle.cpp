@@ -127,7 +127,8 @@ inline Block rng_block(uint32_t pixel, uint32_t sample, uint32_t block, uint32_t
     uint32_t v[4] = {pixel, sample, block, key};
     pcg4d(v);
     Block b;
-    for (int i = 0; i < 4; i++) b.u[i] = (float)(v[i] >> 8) * (1.0f / 16777216.0f);  // U[0,1), 24 bit
+    // U[0, 1 - 2^-24]: the scale (1 - 2^-24) 2^-32 keeps a word that rounds up to 2^32 below 1
+    for (int i = 0; i < 4; i++) b.u[i] = (float)v[i] * 0x1.fffffep-33f;
     return b;
 }
 // camera block: lowbias32 (Wellons) of the sample index offset by a per-pixel seed, split into
