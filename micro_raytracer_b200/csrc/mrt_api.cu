@@ -628,6 +628,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
                 h += t.substr(2) + "\n";
             }
         }
+        if (s->sky_color[0] == 0.0f && s->sky_color[1] == 0.0f && s->sky_color[2] == 0.0f) h += "#define MRT_JIT_SKY_BLACK 1\n";
         h += "#define MRT_JIT_N_BOX " + std::to_string(cnt[K_BOX] + cnt[K_BOX_XF]) + "\n";
         h += "#define MRT_JIT_N_SPHERE " + std::to_string(cnt[K_SPHERE]) + "\n";
         h += "#define MRT_JIT_N_PLANE " + std::to_string(cnt[K_PLANE]) + "\n";

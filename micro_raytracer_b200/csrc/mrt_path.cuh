@@ -65,8 +65,10 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
         const bool hit = closest_hit<V, F, false, (F & F_TRANSMIT) != 0>(sc, o, d, &h);
         if (!hit) {
             // primary miss: sky.color (rt.rs:958); later miss: fold seed sky.color*sky.pwr (rt.rs:964)
+#if !(defined(MRT_JIT) && defined(MRT_JIT_SKY_BLACK))  // a black sky adds nothing: compiled out when the scene says so
             if (bounce == 0) acc = acc + mk(c.sky[0], c.sky[1], c.sky[2]);
             else acc = acc + T * mk(c.sky_tail[0], c.sky_tail[1], c.sky_tail[2]);
+#endif
             bounce = 0xffffffffu; j++;
             continue;
         }
@@ -161,7 +163,9 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
                 // a NaN direction (|n + r v| = 0) would poison the lane: end the path as a miss
                 const bool bad = !(fabsf(d.x) <= 2.0f);
                 if (bounce > fp.max_bounce || bad) {  // rt.rs:1018
+#if !(defined(MRT_JIT) && defined(MRT_JIT_SKY_BLACK))
                     acc = acc + T * mk(c.sky_tail[0], c.sky_tail[1], c.sky_tail[2]);
+#endif
                     bounce = 0xffffffffu; j++;
                 }
             }
