@@ -628,6 +628,14 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
                 h += t.substr(2) + "\n";
             }
         }
+        {
+            bool binary = true;
+            for (uint32_t oi = 0; oi < s->n_objects; oi++) {
+                const mrt_material& m = s->objects[oi].mat;
+                binary &= (m.emit == 0.0f || m.emit == 1.0f) && m.emap < 0;
+            }
+            if (binary) h += "#define MRT_JIT_EMIT_BINARY 1\n";
+        }
         if (s->sky_color[0] == 0.0f && s->sky_color[1] == 0.0f && s->sky_color[2] == 0.0f) h += "#define MRT_JIT_SKY_BLACK 1\n";
         h += "#define MRT_JIT_N_BOX " + std::to_string(cnt[K_BOX] + cnt[K_BOX_XF]) + "\n";
         h += "#define MRT_JIT_N_SPHERE " + std::to_string(cnt[K_SPHERE]) + "\n";

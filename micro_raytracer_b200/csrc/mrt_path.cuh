@@ -134,7 +134,12 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
             }
 
             // ---- RayTracer::reduce_light, rt.rs:956-994, evaluated forward
+#if defined(MRT_JIT) && defined(MRT_JIT_EMIT_BINARY)
+            // every emit of the scene is 0 or 1 (no emap): gen_bool(1) is always true, gen_bool(0) never — no draw needed
+            if (m.emit != 0.0f) {
+#else
             if ((float)uw.w * MRT_U32_TO_UNIT < m.emit) {  // emission draw, rt.rs:966-970
+#endif
                 acc = acc + T * m.color;
                 bounce = 0xffffffffu; j++;
                 continue;
