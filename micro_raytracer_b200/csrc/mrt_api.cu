@@ -413,6 +413,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     std::vector<uint32_t> oi_k[K_NKIND];
     std::vector<Xf> mesh_m;
     std::vector<BxfInst> bxf;
+    int rot_class = 0;  // MRT_JIT_ROT: 0 no rotated instance, 1 yaw-only, 2 general
     std::vector<PrimBox> prim_boxes;  // finite instances, for the scene-level BVH
     bool prim_boxes_ok = true;
     for (uint32_t oi = 0; oi < s->n_objects; oi++) {
@@ -442,6 +443,10 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
             const HM M = transform_of(nd);
             if (!finite_m(M)) return fail(c, MRT_ERR_INVALID, "instance dir gives a non-finite transform (|w| > 1, zero or vertical facing vector)");
             const bool ident = is_identity(M);
+            if (!ident) {
+                const bool yaw = M.m[2] == 0.0f && M.m[5] == 0.0f && M.m[6] == 0.0f && M.m[7] == 0.0f && M.m[8] == 1.0f;
+                rot_class = std::max(rot_class, yaw ? 1 : 2);
+            }
             const H3 pos = {in.pos[0], in.pos[1], in.pos[2]};
             SlimInst si{};
             FatInst fi{};
@@ -637,6 +642,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
             if (binary) h += "#define MRT_JIT_EMIT_BINARY 1\n";
         }
         if (s->sky_color[0] == 0.0f && s->sky_color[1] == 0.0f && s->sky_color[2] == 0.0f) h += "#define MRT_JIT_SKY_BLACK 1\n";
+        h += "#define MRT_JIT_ROT " + std::to_string(rot_class) + "\n";
         h += "#define MRT_JIT_N_BOX " + std::to_string(cnt[K_BOX] + cnt[K_BOX_XF]) + "\n";
         h += "#define MRT_JIT_N_SPHERE " + std::to_string(cnt[K_SPHERE]) + "\n";
         h += "#define MRT_JIT_N_PLANE " + std::to_string(cnt[K_PLANE]) + "\n";

@@ -725,18 +725,35 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
 }
 
 // ------------------------------------------------------------------ per-hit data of the winner
+// What the specialised kernel knows about instance rotations (MRT_JIT_ROT): 0 = no instance is
+// rotated, 1 = every rotated instance is yaw-only (M = [[a,b,0],[c,d,0],[0,0,1]]), 2 = anything.
+#if defined(MRT_JIT) && defined(MRT_JIT_ROT)
+#define MRT_ROT MRT_JIT_ROT
+#else
+#define MRT_ROT 2
+#endif
 struct Surf {
     float4 P, A, m0, m1, m2;
     __device__ __forceinline__ uint32_t flags() const { return __float_as_uint(P.w); }
     __device__ __forceinline__ uint32_t kind() const { return flags() & 0xffu; }
-    __device__ __forceinline__ bool identity() const { return (flags() & FAT_IDENT) != 0u; }
+    __device__ __forceinline__ bool identity() const { return MRT_ROT == 0 || (flags() & FAT_IDENT) != 0u; }
     __device__ __forceinline__ bool textured() const { return (flags() & FAT_TEX) != 0u; }
-    __device__ __forceinline__ bool normal_xf() const { return (flags() & FAT_NXF) != 0u; }
+    __device__ __forceinline__ bool normal_xf() const { return MRT_ROT != 0 && (flags() & FAT_NXF) != 0u; }
 };
+// M v with what MRT_ROT allows to skip
+__device__ __forceinline__ f3 mulM_rot(const Surf& s, f3 v) {
+#if MRT_ROT == 1
+    return {fmaf(s.m0.y, v.y, s.m0.x * v.x), fmaf(s.m1.y, v.y, s.m1.x * v.x), v.z};
+#else
+    return {dot(xyz(s.m0), v), dot(xyz(s.m1), v), dot(xyz(s.m2), v)};
+#endif
+}
 __device__ __forceinline__ void load_surf(const FatInst* f, Surf* s) {
     s->P = __ldg(&f->P);
     s->A = __ldg(&f->A);
-    if ((s->flags() & (FAT_IDENT | FAT_TEX)) != FAT_IDENT) {  // rows only when rotated or textured (ids live in .w)
+    // rows only when rotated or textured (the texture ids live in .w)
+    const bool rows = (MRT_ROT == 0) ? (s->flags() & FAT_TEX) != 0u : (s->flags() & (FAT_IDENT | FAT_TEX)) != FAT_IDENT;
+    if (rows) {
         s->m0 = __ldg(&f->m0);
         s->m1 = __ldg(&f->m1);
         s->m2 = __ldg(&f->m2);
@@ -753,7 +770,7 @@ __device__ __forceinline__ void load_surf(const FatInst* f, Surf* s) {
 // object-space hit point minus instance pos: rot_y * (look * (hp - pos)), rt.rs:782
 __device__ __forceinline__ f3 to_local(const Surf& s, f3 hp) {
     f3 r = hp - xyz(s.P);
-    return s.identity() ? r : mulM(s.m0, s.m1, s.m2, r);
+    return s.identity() ? r : mulM_rot(s, r);
 }
 // Box::normal, rt.rs:414-445, on p = local point * 2/size: windows |p_i| in 1 +- E, checked
 // x, -x, y, -y, then — the missing `else` at :435 — an independent z test that overrides.
@@ -798,7 +815,7 @@ __device__ __forceinline__ f3 surf_normal(const SceneCommon& c, const Surf& s, f
         const DTri* tp = &c.tri[__float_as_uint(s.A.x) + (uint32_t)tri];
         n = cross(xyz(__ldg(&tp->e0)), xyz(__ldg(&tp->e1)));  // rt.rs:459-466
     } else n = box_face(pl * xyz(s.A));
-    if (s.normal_xf()) n = mulM(s.m0, s.m1, s.m2, n);  // MRT_OPT_NORMAL_SPACE
+    if (s.normal_xf()) n = mulM_rot(s, n);  // MRT_OPT_NORMAL_SPACE
     if (mesh) n = normalize(n);
     return n;
 }
