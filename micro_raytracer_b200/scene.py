@@ -235,6 +235,15 @@ class PackedScene:
         s.sky_pwr = float(scene.sky.pwr)
         self.c = s
 
+    def objects_array(self):
+        return [self.objects[k] for k in range(self.c.n_objects)]
+
+    def instances_array(self):
+        return [self.instances[k] for k in range(self.c.n_instances)]
+
+    def lights_array(self):
+        return [self.lights[k] for k in range(self.c.n_lights)]
+
     def nbytes(self) -> int:
         """Host bytes an mrt_set_scene call copies (for bench.py's h2d accounting)."""
         s = self.c
