@@ -791,8 +791,23 @@ int mrt_execute(mrt_ctx* c, uint32_t n_passes, double* seconds) {
     CK(cudaSetDevice(c->device));
     if (!c->have_scene || !c->have_frame) return fail(c, MRT_ERR_STATE, "execute before set_scene/set_frame");
     CK(cudaEventRecord(c->ev0, c->stream));
-    int rc = mrt_execute_async(c, n_passes);
-    if (rc) return rc;
+    // While the scene-specialised kernel is still compiling (MRT_JIT_AUTO, first big call after
+    // mrt_set_scene), a blocking call feeds the generic kernel in slices of ~2^27 paths and looks
+    // again after each, so a one-shot render (the CLI case) switches over after ~0.15 s instead of
+    // finishing on the slower kernel.  mrt_execute_async cannot wait and keeps what it has.
+    uint32_t left = n_passes;
+    while (left) {
+        uint32_t n = left;
+        const bool pending = c->jit_mode == MRT_JIT_AUTO && !c->jit_header.empty() && !c->jit_kernel && !c->jit_failed;
+        if (pending) {
+            const uint64_t npix = (uint64_t)c->nw * c->nh;
+            n = (uint32_t)std::min<uint64_t>(left, std::max<uint64_t>(1, (1ull << 27) / std::max<uint64_t>(1, npix)));
+        }
+        int rc = mrt_execute_async(c, n);
+        if (rc) return rc;
+        left -= n;
+        if (pending && left) CK(cudaStreamSynchronize(c->stream));
+    }
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaEventSynchronize(c->ev1));
     if (seconds) {
