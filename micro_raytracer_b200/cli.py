@@ -5,7 +5,7 @@ merges them with the same precedence as CLI::parse_render (cli.rs:78-153), and d
 Sampler::{execute, img} exactly like CLI::raytrace (cli.rs:155-177).  SURVEY.md §8(f) "next #2".
 
 Everything is turned into the JSON description first, so the flags and the files share one
-path into scene.render_from_dict.  Not supported: --http (§8f #3).
+path into scene.render_from_dict.  --http ADDRESS starts the endpoint of http.py.
 """
 from __future__ import annotations
 
@@ -188,7 +188,7 @@ def build_parser() -> argparse.ArgumentParser:
     ap.add_argument("--pretty", action="store_true", help="Print full render info in json with prettifier")
     ap.add_argument("-d", "--dry", action="store_true", help="Dry run (useful with verbose)")
     ap.add_argument("-o", "--output", metavar="FILE.EXT", help="Final image output filename")
-    ap.add_argument("--http", metavar="address", help="Launch http server (not supported by this front-end)")
+    ap.add_argument("--http", metavar="address", help="Launch http server")
     ap.add_argument("--bounce", type=int, help="Max ray bounce")
     ap.add_argument("--sample", type=int, help="Max path-tracing samples")
     ap.add_argument("--loss", type=float, help="Ray bounce energy loss")
@@ -288,8 +288,10 @@ def main(argv: Optional[List[str]] = None) -> int:
     argv = sys.argv[1:] if argv is None else argv
     try:
         ns, d, render = parse_render(argv)
-        if ns.http:
-            raise CliError("--http is not supported by this front-end (SURVEY.md §8f #3)")
+        if ns.http:  # raytrace.rs:22-30: blocks forever
+            from .http import serve
+            serve(ns.http, ns.device)
+            return 0
         log = (lambda m: print(m, flush=True)) if ns.verbose else None
         if ns.verbose:
             print(json.dumps(d, indent=2 if ns.pretty else None))
