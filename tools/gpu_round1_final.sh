@@ -11,4 +11,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:path_kernel_jit -c 1 -f -o gpurun_out/r1_path_kernel_jit python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r1_ncu_full.log 2>&1
 tail -2 gpurun_out/r1_ncu_full.log
 python tools/bench_scenes.py --cpu > gpurun_out/r1_scenes.jsonl 2> gpurun_out/r1_scenes.err; cat gpurun_out/r1_scenes.jsonl
-./tools/microbench > gpurun_out/r1_microbench.txt 2>&1
+nvcc -O3 -gencode arch=compute_100a,code=sm_100a -ftz=true -o tools/microbench tools/microbench.cu && ./tools/microbench > gpurun_out/r1_microbench.txt 2>&1
