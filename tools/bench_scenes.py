@@ -31,7 +31,8 @@ def main():
         s = mrt.Sampler(device=0)
         s.execute(r.scene, r.frame, r.rt, 1)  # upload + warm-up; starts the background scene specialisation
         t_wait = time.time()
-        while s.jit_status()["eligible"] and not s.jit_status()["compiled"] and time.time() - t_wait < 5.0:
+        while (os.environ.get("MRT_JIT", "1") != "0" and s.jit_status()["eligible"] and not s.jit_status()["compiled"]
+               and time.time() - t_wait < 5.0):
             s.execute(r.scene, r.frame, r.rt, 1)  # polls the compile; gives up quietly when NVRTC is unavailable / disabled
             time.sleep(0.02)
         nw, nh, _ = s.film_size()
