@@ -1,0 +1,159 @@
+//! Drop-in replacement of the reference's src/sampler.rs: the same `Sampler::{new, execute, img}`
+//! (sampler.rs:19,28,80) over the CUDA library.  The thread pool, the per-tile HashMap merge and the
+//! tone map / Lanczos resize all happen on the GPU behind `mrt_execute` / `mrt_img`.
+use image::RgbImage;
+use std::ffi::CStr;
+use std::time::Duration;
+
+use crate::mrt_sys::*;
+use crate::rt::{Frame, LightKind, Material, RayTracer, RendererKind, Scene, Texture};
+
+pub struct Sampler {
+    ctx: *mut mrt_ctx,
+    scene_key: usize,            // address of the Scene last uploaded (execute borrows it immutably, sampler.rs:28)
+    frame_key: Option<mrt_frame>,
+    rt_key: (usize, u32),
+}
+
+unsafe impl Send for Sampler {}  // one context per thread, like `&mut self` (http.rs:138,155)
+
+fn last_error(ctx: *const mrt_ctx) -> String {
+    unsafe { CStr::from_ptr(mrt_last_error(ctx)).to_string_lossy().into_owned() }
+}
+
+/// Owns the flat arrays an `mrt_scene` points into for the duration of `mrt_set_scene` (which copies).
+struct Packed {
+    objects: Vec<mrt_object>, instances: Vec<mrt_instance>, textures: Vec<mrt_texture>, texels: Vec<f32>,
+    meshes: Vec<mrt_mesh>, triangles: Vec<f32>, lights: Vec<mrt_light>,
+}
+
+impl Packed {
+    fn tex_id(&mut self, t: &Option<Texture>) -> i32 {
+        match t {
+            None => -1,
+            Some(t) => {
+                let first = (self.texels.len() / 3) as u64;
+                if let Some(dat) = &t.dat {
+                    for c in dat { self.texels.extend_from_slice(&[c.x, c.y, c.z]); }
+                }
+                self.textures.push(mrt_texture { w: t.w as u32, h: t.h as u32, first_texel: first,
+                                                 has_dat: t.dat.is_some() as u32, _pad: 0 });
+                (self.textures.len() - 1) as i32
+            }
+        }
+    }
+
+    fn material(&mut self, m: &Material) -> mrt_material {
+        mrt_material {
+            albedo: [m.albedo.x, m.albedo.y, m.albedo.z],
+            rough: m.rough, metal: m.metal, glass: m.glass, opacity: m.opacity, emit: m.emit,
+            tex: self.tex_id(&m.tex), rmap: self.tex_id(&m.rmap), mmap: self.tex_id(&m.mmap),
+            gmap: self.tex_id(&m.gmap), omap: self.tex_id(&m.omap), emap: self.tex_id(&m.emap),
+        }
+    }
+
+    fn new(scene: &Scene) -> Packed {
+        let mut p = Packed { objects: vec![], instances: vec![], textures: vec![], texels: vec![],
+                             meshes: vec![], triangles: vec![], lights: vec![] };
+        for r in scene.renderer.iter().flatten() {
+            let mut o = mrt_object { kind: 0, mesh: 0, param: [0.0; 9], first_inst: p.instances.len() as u32,
+                                     n_inst: r.instance.len() as u32, mat: p.material(&r.mat) };
+            match &r.kind {
+                RendererKind::Sphere(s) => { o.kind = MRT_SPHERE; o.param[0] = s.0; }
+                RendererKind::Plane(n) => { o.kind = MRT_PLANE; o.param[..3].copy_from_slice(&[n.0.x, n.0.y, n.0.z]); }
+                RendererKind::Box(b) => { o.kind = MRT_BOX; o.param[..3].copy_from_slice(&[b.0.x, b.0.y, b.0.z]); }
+                RendererKind::Triangle(t) => {
+                    o.kind = MRT_TRIANGLE;
+                    o.param.copy_from_slice(&[t.0.x, t.0.y, t.0.z, t.1.x, t.1.y, t.1.z, t.2.x, t.2.y, t.2.z]);
+                }
+                RendererKind::Mesh(m) => {
+                    o.kind = MRT_MESH;
+                    o.mesh = p.meshes.len() as u32;
+                    p.meshes.push(mrt_mesh { first_tri: (p.triangles.len() / 9) as u32, n_tri: m.mesh.len() as u32 });
+                    for t in &m.mesh {   // the depth-3 octree (parser.rs:805-824) is rebuilt inside the library
+                        p.triangles.extend_from_slice(&[t.0.x, t.0.y, t.0.z, t.1.x, t.1.y, t.1.z, t.2.x, t.2.y, t.2.z]);
+                    }
+                }
+            }
+            for i in &r.instance {
+                p.instances.push(mrt_instance { pos: [i.pos.x, i.pos.y, i.pos.z], dir: [i.dir.w, i.dir.x, i.dir.y, i.dir.z] });
+            }
+            p.objects.push(o);
+        }
+        for l in scene.light.iter().flatten() {
+            let (kind, v) = match l.kind {
+                LightKind::Point { pos } => (MRT_LIGHT_POINT, pos),
+                LightKind::Dir { dir } => (MRT_LIGHT_DIR, dir),
+            };
+            p.lights.push(mrt_light { kind, v: [v.x, v.y, v.z], pwr: l.pwr, color: [l.color.x, l.color.y, l.color.z] });
+        }
+        p
+    }
+
+    fn view(&self, scene: &Scene) -> mrt_scene {
+        mrt_scene {
+            objects: self.objects.as_ptr(), n_objects: self.objects.len() as u32,
+            instances: self.instances.as_ptr(), n_instances: self.instances.len() as u32,
+            textures: self.textures.as_ptr(), n_textures: self.textures.len() as u32,
+            texels: self.texels.as_ptr(), n_texels: (self.texels.len() / 3) as u64,
+            meshes: self.meshes.as_ptr(), n_meshes: self.meshes.len() as u32,
+            triangles: self.triangles.as_ptr(), n_triangles: (self.triangles.len() / 9) as u32,
+            lights: self.lights.as_ptr(), n_lights: self.lights.len() as u32,
+            sky_color: [scene.sky.color.x, scene.sky.color.y, scene.sky.color.z], sky_pwr: scene.sky.pwr,
+        }
+    }
+}
+
+fn pack_frame(f: &Frame) -> mrt_frame {
+    let c = &f.cam;
+    mrt_frame { res: [f.res.0, f.res.1], ssaa: f.ssaa, cam_pos: [c.pos.x, c.pos.y, c.pos.z],
+                cam_dir: [c.dir.w, c.dir.x, c.dir.y, c.dir.z], fov: c.fov, gamma: c.gamma, exp: c.exp, aprt: c.aprt, foc: c.foc }
+}
+
+impl Sampler {
+    /// `workers` / `n_dim` (--worker / --dim) are accepted and ignored: the CUDA grid replaces the tile pool.
+    pub fn new(workers: u32, n_dim: usize) -> Sampler {
+        let mut ctx = std::ptr::null_mut();
+        let rc = unsafe { mrt_create(&mut ctx, 0, workers, n_dim as u32) };
+        if rc != MRT_OK { panic!("mrt_create: {}", last_error(std::ptr::null())); }   // Sampler::new is infallible
+        Sampler { ctx, scene_key: 0, frame_key: None, rt_key: (usize::MAX, 0) }
+    }
+
+    fn check(&self, rc: i32) { if rc != MRT_OK { panic!("mrt: {}", last_error(self.ctx)); } }  // execute is infallible too
+
+    /// One pass = one path per supersampled pixel, accumulated on the device (sampler.rs:28-78).
+    pub fn execute<'a>(&mut self, scene: &'a Scene, frame: &Frame, rt: &'a RayTracer) -> Duration {
+        let key = scene as *const Scene as usize;
+        if key != self.scene_key {
+            let packed = Packed::new(scene);
+            let view = packed.view(scene);
+            self.check(unsafe { mrt_set_scene(self.ctx, &view) });
+            self.scene_key = key;
+        }
+        let f = pack_frame(frame);
+        if self.frame_key != Some(f) {
+            self.check(unsafe { mrt_set_frame(self.ctx, &f) });
+            self.frame_key = Some(f);
+        }
+        let rk = (rt.bounce, rt.loss.to_bits());
+        if rk != self.rt_key {
+            self.check(unsafe { mrt_set_rt(self.ctx, rt.bounce as u32, rt.loss, 0x5EED) });
+            self.rt_key = rk;
+        }
+        let mut seconds = 0f64;
+        self.check(unsafe { mrt_execute(self.ctx, 1, &mut seconds) });
+        Duration::from_secs_f64(seconds)
+    }
+
+    /// ÷passes, powf(gamma), Reinhard, `as u8`, Lanczos3 to `res` — all on the device (sampler.rs:80-99).
+    pub fn img(&self, frame: &Frame) -> Result<RgbImage, String> {
+        let (w, h) = (frame.res.0 as u32, frame.res.1 as u32);
+        let mut buf = vec![0u8; w as usize * h as usize * 3];
+        if unsafe { mrt_img(self.ctx, buf.as_mut_ptr()) } != MRT_OK { return Err(last_error(self.ctx)); }
+        RgbImage::from_raw(w, h, buf).ok_or_else(|| "image size mismatch".to_string())
+    }
+}
+
+impl Drop for Sampler {
+    fn drop(&mut self) { unsafe { mrt_destroy(self.ctx) } }
+}
