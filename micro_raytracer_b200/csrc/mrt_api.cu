@@ -579,11 +579,33 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
         // box pairs: X = packed FFMA2 pair, XS = the two boxes one at a time, X1 = single box (odd count).
         // A pair constant whose two lanes differ costs two uniform-register moves per use in the packed form
         // (only equal lanes are an immediate broadcast), so lopsided pairs are cheaper unpacked.
-        h += "#define MRT_JIT_BOXPAIRS(X, XS, X1)";
+        h += "#define MRT_JIT_BOXPAIRS(X, XS, X1, CB, CE)";
+        // scenes of many boxes: consecutive pairs are bracketed, four at a time, by their bounding box
+        // (declaration order is kept, so the first-minimum rule is untouched)
+        size_t cluster = 4;
+        if (const char* e = std::getenv("MRT_JIT_CLUSTER")) cluster = (size_t)std::max(0, std::atoi(e));  // experiment knob, 0 = off
+        const bool clustered = cluster > 0 && boxp.size() >= 3 * cluster;
         for (size_t k = 0; k < boxp.size(); k++) {
             const float* q = &boxp[k].q0.x;  // (cA.x,cB.x, cA.y,cB.y, cA.z,cB.z, hA.x,hB.x, hA.y,hB.y, hA.z,hB.z)
             ok &= all_finite(q, 12);
             const bool odd = 2 * k + 1 >= by_kind[K_BOX].size();
+            if (clustered && k % cluster == 0) {
+                float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+                for (size_t j = k; j < std::min(boxp.size(), k + cluster); j++) {
+                    const float* p = &boxp[j].q0.x;
+                    const int lanes = (2 * j + 1 >= by_kind[K_BOX].size()) ? 1 : 2;
+                    for (int l = 0; l < lanes; l++)
+                        for (int a = 0; a < 3; a++) {
+                            lo[a] = std::fmin(lo[a], p[2 * a + l] - std::fabs(p[6 + 2 * a + l]));
+                            hi[a] = std::fmax(hi[a], p[2 * a + l] + std::fabs(p[6 + 2 * a + l]));
+                        }
+                }
+                const float v[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
+                ok &= all_finite(v, 6);
+                std::string t;
+                lits(&t, v, 6);
+                h += " CB(" + t.substr(2) + ")";
+            }
             int packed = 6, scalar = 12;
             for (int a = 0; a < 3; a++) {
                 const float ca = q[2 * a], cb = q[2 * a + 1], ha = q[6 + 2 * a], hb = q[7 + 2 * a];
@@ -595,6 +617,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
             h += std::to_string(k);
             lits(&h, q, 12);
             h += ")";
+            if (clustered && (k % cluster == cluster - 1 || k + 1 == boxp.size())) h += " CE";
         }
         h += "\n";
         tab("MRT_JIT_SPHERES", by_kind[K_SPHERE].size(), [&](size_t k) {

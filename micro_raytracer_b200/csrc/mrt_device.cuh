@@ -670,7 +670,13 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
 #define J_MSH(k, px, py, pz, rot, mid, m0, m1, m2, m3, m4, m5, m6, m7, m8, m9, m10, m11) \
     if constexpr ((F & F_MESH) != 0) { const Xf x__ = {{m0, m1, m2, m3, m4, m5, m6, m7, m8, m9, m10, m11}}; \
         test_mesh<F, ANY, WANT_T1, false>(B, c, r, SlimInst{make_float4(px, py, pz, 0.0f), make_float4(__uint_as_float(rot), __uint_as_float(mid), 0.0f, 0.0f)}, x__, (int)(MRT_JIT_FIRST_MESH + (k))); }
-        MRT_JIT_BOXPAIRS(J_BOXP, J_BOXS, J_BOX1)
+        // J_CB / J_CE bracket a cluster of consecutive boxes with its bounding box (big scenes only): the
+        // cluster is skipped when the ray misses the box or enters it behind the best hit so far
+#define J_CB(lx, ly, lz, hx, hy, hz) { float tn__; if (node_hit(r, make_float4(lx, ly, lz, 0.0f), make_float4(hx, hy, hz, 0.0f), ANY ? __int_as_float(0x7f800000) : B.t0, &tn__)) {
+#define J_CE }}
+        MRT_JIT_BOXPAIRS(J_BOXP, J_BOXS, J_BOX1, J_CB, J_CE)
+#undef J_CB
+#undef J_CE
         MRT_JIT_SPHERES(J_SPH)
         MRT_JIT_PLANES(J_PLN)
         MRT_JIT_BXFS(J_BXF)

@@ -7,7 +7,7 @@ DEFAULT = """
 #define MRT_JIT_N_BOX 3
 #define MRT_JIT_N_SPHERE 1
 #define MRT_JIT_N_PLANE 1
-#define MRT_JIT_BOXPAIRS(X, XS, X1) XS(1, 0x1p+0f,0x1p+1f,0x0p+0f,0x1p+0f,0x1p+0f,0x0p+0f,0x1p-1f,0x1p-2f,0x1p-1f,0x1p-1f,0x1p-1f,0x1p-3f) X1(2, 0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p-1f,-0x1p+0f,0x1p-1f,-0x1p+0f,0x1p-1f,-0x1p+0f) X(0, 0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p-1f,0x1p-1f,0x1p-1f,0x1p-1f,0x1p-1f,-0x1p+0f)
+#define MRT_JIT_BOXPAIRS(X, XS, X1, CB, CE) CB(-0x1p+2f,-0x1p+2f,-0x1p+2f,0x1p+2f,0x1p+2f,0x1p+2f) XS(1, 0x1p+0f,0x1p+1f,0x0p+0f,0x1p+0f,0x1p+0f,0x0p+0f,0x1p-1f,0x1p-2f,0x1p-1f,0x1p-1f,0x1p-1f,0x1p-3f) X1(2, 0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p-1f,-0x1p+0f,0x1p-1f,-0x1p+0f,0x1p-1f,-0x1p+0f) CE X(0, 0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p+0f,0x1p-1f,0x1p-1f,0x1p-1f,0x1p-1f,0x1p-1f,-0x1p+0f)
 #define MRT_JIT_SPHERES(X) X(0, 0x1p+0f, 0x1p+1f, 0x1p+0f, 0x1p-2f)
 #define MRT_JIT_PLANES(X) X(0, 0x0p+0f, 0x0p+0f, 0x1p+0f, -0x1p+0f)
 #define MRT_JIT_BXFS(X) X(0, 0x1p-1f,0x1p-1f,0x0p+0f,0x1p+0f, -0x1p-1f,0x1p-1f,0x0p+0f,0x1p+0f, 0x0p+0f,0x0p+0f,0x1p+0f,0x1p+0f, 0x1p-2f,0x1p-2f,0x1p-2f)
