@@ -602,6 +602,10 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
                             hi[a] = std::fmax(hi[a], p[2 * a + l] + std::fabs(p[6 + 2 * a + l]));
                         }
                 }
+                for (int a = 0; a < 3; a++) {  // the cluster test and the box tests round differently: keep a margin
+                    const float pad = 1e-5f * (std::fabs(lo[a]) + std::fabs(hi[a])) + 1e-6f;
+                    lo[a] -= pad; hi[a] += pad;
+                }
                 const float v[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
                 ok &= all_finite(v, 6);
                 std::string t;

@@ -409,3 +409,35 @@ def test_full_size_film_properties():
         ref[jit] = acc
     close = np.abs(ref[JIT_FORCE] - ref[JIT_OFF]).max(axis=2) <= 2e-5 + 2e-4 * np.abs(ref[JIT_OFF]).max(axis=2)
     assert close.mean() >= 0.99999
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_cluster_culling_in_the_specialised_kernel_changes_nothing(seed, monkeypatch, tmp_path):
+    """Scenes of >= 12 box pairs get every four pairs bracketed by their bounding box in the generated
+    code.  Culling only skips boxes that cannot win: hits and images equal the unclustered kernel's bit
+    for bit, and the oracle's like any other scene."""
+    from micro_raytracer_b200.sampler import JIT_FORCE, OPT_JIT
+    rng = np.random.default_rng(900 + seed)
+    objs = [{"type": "box", "sizes": rng.uniform(0.1, 0.6, 3).round(3).tolist(),
+             "pos": [float(rng.uniform(-2, 2)), float(rng.uniform(0.5, 5)), float(rng.uniform(-1.2, 1.2))],
+             "mat": {"albedo": rng.uniform(0.3, 1, 3).round(3).tolist(), "emit": float(rng.random() < 0.2)}}
+            for _ in range(int(rng.integers(30, 90)))]
+    objs.append({"type": "plane", "n": [0, 0, 1], "pos": [0, 0, -1.3]})
+    r = mrt.render_from_dict({"rt": {"bounce": 4, "sample": 2}, "frame": {"res": [64, 40], "ssaa": 1.5, "cam": {"pos": [0, -1.5, 0.2]}},
+                              "scene": {"renderer": objs, "light": [{"type": "dir", "dir": [0.3, 0.5, -1]}],
+                                        "sky": {"color": [0.3, 0.4, 0.6], "pwr": 0.5}}})
+    monkeypatch.setenv("MRT_JIT_CACHE", str(tmp_path))
+    res = {}
+    for cl in ("4", "0"):
+        monkeypatch.setenv("MRT_JIT_CLUSTER", cl)
+        s = mrt.Sampler(device=0)
+        s.set_option(OPT_JIT, JIT_FORCE)
+        s.execute(r.scene, r.frame, r.rt, 2)
+        assert s.jit_status()["compiled"]
+        res[cl] = s.accum()[0]
+    assert np.array_equal(res["4"], res["0"])
+    cpu = oracle_lib.OracleSampler()
+    cpu.execute(r.scene, r.frame, r.rt, 2)
+    ac = cpu.accum()[0]
+    ok = np.abs(res["4"] - ac).max(axis=2) <= 2e-3 + 3e-3 * np.abs(ac).max(axis=2)
+    assert ok.mean() >= 0.95
