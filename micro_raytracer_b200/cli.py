@@ -113,8 +113,9 @@ def light_from_args(args: List[str]) -> dict:  # parser.rs:352-403
         if light["type"] == "point" and p in ("pt:", "point:"):
             light["pos"] = _vec(it, 3)
         elif light["type"] == "dir" and p == "dir:":
-            v = np.asarray(_vec(it, 3), np.float32)
-            light["dir"] = (v * np.float32(1.0) / np.sqrt(np.float32(v @ v))).astype(np.float32).tolist()  # .norm(), parser.rs:383
+            x, y, z = (np.float32(c) for c in _vec(it, 3))
+            r = np.float32(1.0) / np.sqrt(x * x + y * y + z * z)  # Vec3f::norm = self * mag().recip(), lin.rs:60-66 (parser.rs:383)
+            light["dir"] = [float(x * r), float(y * r), float(z * r)]
         elif p == "col:":
             light["color"] = _color(it)
         elif p == "pwr:":

@@ -1,0 +1,75 @@
+// raytrace.cpp — the native `raytrace` front-end: the reference's binary (src/bin/raytrace.rs:12-57)
+// and render loop (CLI::raytrace, src/cli.rs:155-177) over the CUDA path.  Same flags, same JSON,
+// same `key: v v v` mini-grammar; the pixels come from libmrt.so (sm_100a kernels), never from
+// the CPU.  SURVEY.md §8(f) "next #2" (front-end) and "#3" (--http).
+#include <chrono>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+
+#include "http.hpp"
+#include "image_io.hpp"
+#include "parser.hpp"
+
+using namespace mrt_host;
+
+static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// CLI::raytrace, cli.rs:155-177: one Sampler, rt.sample passes, optional save per pass, final save
+static double raytrace(const CliArgs& a, const Render& render, const Logger& log) {
+    Sampler sampler((uint32_t)a.worker.value_or(24), (uint32_t)a.dim.value_or(64), a.device, a.seed);
+    const std::string out = a.output.value_or("out.png");
+    const double t0 = now();
+    if (a.update) {
+        for (uint32_t n = 0; n < render.rt.sample; n++) {
+            const double dt = sampler.execute(render.scene, render.frame, render.rt);
+            if (log) log("cli:sample:" + std::to_string(n) + ": " + std::to_string(dt) + "s");
+            save_image(sampler.img(render.frame), out);
+        }
+    } else if (render.rt.sample > 0) {
+        // without --update nothing observes the accumulator between passes: one call renders them all
+        const double dt = sampler.execute(render.scene, render.frame, render.rt, render.rt.sample);
+        if (log) log("cli:sample:0.." + std::to_string(render.rt.sample - 1) + ": " + std::to_string(dt) + "s");
+    }
+    save_image(sampler.img(render.frame), out);
+    return now() - t0;
+}
+
+int main(int argc, char** argv) {
+    std::vector<std::string> args(argv + 1, argv + argc);
+    try {
+        if (args.size() == 3 && args[0] == "--convert") {  // test hook for the encoders: RGB8 image in, format by extension out
+            save_image(load_image_rgb8(args[1]), args[2]);
+            return 0;
+        }
+        const CliArgs a = parse_cli(args);
+        Logger log;
+        if (a.verbose) log = [](const std::string& m) { std::cout << m << std::endl; };
+        if (a.http) {  // raytrace.rs:22-30: blocks forever
+            serve(*a.http, a.device, log ? log : Logger([](const std::string& m) { std::cout << m << std::endl; }));
+            return 0;
+        }
+        const Json d = merged_description(a);
+        const std::string base = dirname_of(a.full ? *a.full : a.scene ? *a.scene : std::string("./x"));
+        const Render render = render_from_json(d, base);
+        if (a.verbose) std::cout << d.dump(a.pretty ? 2 : -1) << std::endl;  // raytrace.rs:36-40
+        if (a.dump_packed) {  // test hook: the flat C-ABI arrays this description packs to
+            const PackedScene p(render.scene);
+            const mrt_frame f = render.frame.pack();
+            std::ofstream o(*a.dump_packed, std::ios::binary);
+            const std::string s = p.bytes();
+            o.write(s.data(), (std::streamsize)s.size());
+            o.write(reinterpret_cast<const char*>(&f), sizeof f);
+            o.write(reinterpret_cast<const char*>(&render.rt.bounce), 4);
+            o.write(reinterpret_cast<const char*>(&render.rt.sample), 4);
+            o.write(reinterpret_cast<const char*>(&render.rt.loss), 4);
+        }
+        if (a.dry) return 0;  // raytrace.rs:42
+        const double dt = raytrace(a, render, log);
+        if (log) log("cli:done: " + std::to_string(dt) + "s");
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "cli: %s\n", e.what());  // raytrace.rs:55
+        return 1;
+    }
+}
