@@ -108,6 +108,9 @@ struct mrt_ctx {
     DevBuf<DMeshLeaf> d_leaf;
     DevBuf<uint32_t> d_leaf_idx;
     DevBuf<DTri> d_tri;
+    DevBuf<BvhNode> d_tbvh;          // triangle BVHs of the meshes
+    DevBuf<uint32_t> d_tbvh_ref;
+    DevBuf<DTriLeaf> d_tri_leaf;     // per triangle: the octree leaves that list it
     DevBuf<uint32_t> d_obj_inst;
 
     // frame / rt
@@ -333,7 +336,7 @@ void mrt_destroy(mrt_ctx* c) {
     if (c->jit_requested && !c->jit_header.empty()) mrt_jit_wait(c->jit_header);
     for (auto& b : c->d_slim) b.release();
     c->d_boxp.release(); c->d_bvh.release(); c->d_bvh_ref.release(); c->d_bxf.release(); c->d_mesh_m.release(); c->d_fat.release(); c->d_tex.release(); c->d_texels.release();
-    c->d_mesh.release(); c->d_leaf.release(); c->d_leaf_idx.release(); c->d_tri.release(); c->d_obj_inst.release();
+    c->d_mesh.release(); c->d_leaf.release(); c->d_leaf_idx.release(); c->d_tri.release(); c->d_tbvh.release(); c->d_tbvh_ref.release(); c->d_tri_leaf.release(); c->d_obj_inst.release();
     c->d_accum.release(); c->d_ss.release(); c->d_out.release(); c->d_tmp.release(); c->d_rgb.release();
     c->d_wv.release(); c->d_wh.release(); c->d_lv.release(); c->d_cv.release(); c->d_lh.release(); c->d_ch.release();
     c->d_hits.release();
@@ -381,6 +384,12 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     std::vector<DMeshLeaf> leaves;
     std::vector<uint32_t> leaf_idx;
     std::vector<DTri> tris;
+    std::vector<BvhNode> tbvh;
+    std::vector<uint32_t> tbvh_ref;
+    std::vector<DTriLeaf> tri_leaf;
+    size_t tbvh_leaf = 1;  // triangles per BVH leaf: 1 measured best (Mesh.json 1418 vs 1377 Mpaths/s with 2, 1247 with 4)
+    if (const char* e = std::getenv("MRT_MESH_BVH_LEAF")) tbvh_leaf = (size_t)std::max(1, std::atoi(e));  // experiment knob
+    const bool mesh_bvh = !std::getenv("MRT_NO_MESH_BVH");  // test knob: the sequential leaf walk instead
     for (uint32_t i = 0; i < s->n_meshes; i++) {
         const mrt_mesh& m = s->meshes[i];
         if ((uint64_t)m.first_tri + m.n_tri > s->n_triangles) return fail(c, MRT_ERR_INVALID, "mesh triangle range out of bounds");
@@ -390,7 +399,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
         float root_half[3];
         build_leaves(tp, m.n_tri, &lb, root_half);
         if (lb.empty()) return fail(c, MRT_ERR_INVALID, "mesh octree is empty (the reference would panic, rt.rs:717)");
-        meshes[i] = {(uint32_t)leaves.size(), (uint32_t)lb.size(), (uint32_t)tris.size(), m.n_tri, {root_half[0], root_half[1], root_half[2]}, 0.0f};
+        meshes[i] = {(uint32_t)leaves.size(), (uint32_t)lb.size(), (uint32_t)tris.size(), m.n_tri, {root_half[0], root_half[1], root_half[2]}, 0xffffffffu};
         for (const LeafBuild& l : lb) {
             DMeshLeaf dl;
             dl.lo = make_float4(l.center.x - 0.5f * l.size.x, l.center.y - 0.5f * l.size.y, l.center.z - 0.5f * l.size.z, u2f((uint32_t)leaf_idx.size()));
@@ -398,13 +407,50 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
             leaves.push_back(dl);
             leaf_idx.insert(leaf_idx.end(), l.idx.begin(), l.idx.end());
         }
+        // per triangle: its occurrences in the candidate sequence (leaf order, then list order), ascending
+        std::vector<std::vector<DTriLeaf>> occ(m.n_tri);
+        {
+            size_t listed = 0;
+            for (const LeafBuild& l : lb) listed += l.idx.size();
+            uint32_t rank = (uint32_t)(leaf_idx.size() - listed);  // = this mesh's first position in leaf_idx
+            for (size_t l = 0; l < lb.size(); l++)
+                for (uint32_t ti : lb[l].idx) occ[ti].push_back(DTriLeaf{(uint32_t)(meshes[i].first_leaf + l), rank++});
+        }
         for (uint32_t t = 0; t < m.n_tri; t++) {
             const float* p = tp + 9 * (size_t)t;
             DTri d;
-            d.v0 = make_float4(p[0], p[1], p[2], 0.0f);
-            d.e0 = make_float4(p[3] - p[0], p[4] - p[1], p[5] - p[2], 0.0f);
+            d.v0 = make_float4(p[0], p[1], p[2], u2f((uint32_t)tri_leaf.size()));
+            d.e0 = make_float4(p[3] - p[0], p[4] - p[1], p[5] - p[2], u2f((uint32_t)occ[t].size()));
             d.e1 = make_float4(p[6] - p[0], p[7] - p[1], p[8] - p[2], 0.0f);
             tris.push_back(d);
+            tri_leaf.insert(tri_leaf.end(), occ[t].begin(), occ[t].end());
+        }
+        // triangle BVH (median split, padded boxes: rounding in tri_test must not be able to leave a node).
+        // A triangle no leaf lists can never be a candidate and is left out.
+        meshes[i].bvh_root = 0xffffffffu;
+        if (mesh_bvh && m.n_tri < (1u << 26)) {
+            std::vector<PrimBox> pb;
+            pb.reserve(m.n_tri);
+            bool finite = true;
+            for (uint32_t t = 0; t < m.n_tri; t++) {
+                if (occ[t].empty()) continue;
+                const float* p = tp + 9 * (size_t)t;
+                PrimBox b;
+                for (int a = 0; a < 3; a++) {
+                    const float lo = std::fmin(p[a], std::fmin(p[3 + a], p[6 + a])), hi = std::fmax(p[a], std::fmax(p[3 + a], p[6 + a]));
+                    const float pad = 1e-4f * (std::fabs(lo) + std::fabs(hi)) + 1e-5f;
+                    b.lo[a] = lo - pad; b.hi[a] = hi + pad;
+                    finite &= std::isfinite(b.lo[a]) && std::isfinite(b.hi[a]);
+                }
+                b.ref = t;
+                pb.push_back(b);
+            }
+            if (finite && !pb.empty()) {
+                const size_t root = tbvh.size();
+                tbvh.resize(root + 1);
+                bvh_build(pb, 0, pb.size(), root, &tbvh, &tbvh_ref, tbvh_leaf);
+                meshes[i].bvh_root = (uint32_t)root;
+            }
         }
     }
     // instances, grouped by kind (declaration order inside a kind)
@@ -561,6 +607,9 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     CK(c->d_leaf.upload(leaves));
     CK(c->d_leaf_idx.upload(leaf_idx));
     CK(c->d_tri.upload(tris));
+    CK(c->d_tbvh.upload(tbvh));
+    CK(c->d_tbvh_ref.upload(tbvh_ref));
+    CK(c->d_tri_leaf.upload(tri_leaf));
     CK(c->d_obj_inst.upload(obj_inst));
 
     // ---- text of the scene for the run-time specialised kernel (mrt_jit.cu); small scenes only
@@ -685,6 +734,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     SceneCommon sc{};
     sc.fat = c->d_fat.p; sc.tex = c->d_tex.p; sc.texels = c->d_texels.p;
     sc.mesh = c->d_mesh.p; sc.leaf = c->d_leaf.p; sc.leaf_idx = c->d_leaf_idx.p; sc.tri = c->d_tri.p;
+    sc.tbvh = c->d_tbvh.p; sc.tbvh_ref = c->d_tbvh_ref.p; sc.tri_leaf = c->d_tri_leaf.p;
     sc.n_inst = (uint32_t)fat.size();
     sc.n_lights = s->n_lights;
     for (uint32_t k = 0; k < K_NKIND; k++) { sc.first[k] = first[k]; sc.cnt[k] = cnt[k]; }

@@ -73,8 +73,13 @@ struct BvhNode { float4 lo, hi; };  // lo.w = bits: left child (inner) / first r
 struct DLight { float4 v_kind; float4 color_pwr; };  // v.xyz (pos or unit -dir), w = kind bits ; color.rgb, pwr
 struct DTex { uint32_t w, h, first, has_dat; };      // texel offset into the float4 texel array
 struct DMeshLeaf { float4 lo, hi; };                  // leaf box relative to instance pos; lo.w = first index (bits), hi.w = count (bits)
-struct DMesh { uint32_t first_leaf, n_leaf, first_tri, n_tri; float half[3]; float _pad; };  // half = half extents of the root AABB
-struct DTri { float4 v0, e0, e1; };                   // v0, e0 = v1 - v0, e1 = v2 - v0 (object space, before + pos)
+struct DMesh { uint32_t first_leaf, n_leaf, first_tri, n_tri; float half[3]; uint32_t bvh_root; };  // half = half extents of the root AABB; bvh_root = 0xffffffff: no triangle BVH
+// v0, e0 = v1 - v0, e1 = v2 - v0 (object space, before + pos); v0.w / e0.w (bits) = first entry / entry count of the
+// triangle's DTriLeaf list
+struct DTri { float4 v0, e0, e1; };
+// One octree leaf that lists a triangle: `leaf` indexes SceneCommon::leaf, `rank` is the position of this
+// occurrence in the reference's candidate sequence (leaf order, then list order).  Ascending rank per triangle.
+struct DTriLeaf { uint32_t leaf, rank; };
 
 // capacities of the kernel-parameter scene (constant bank); larger scenes use GlobalScene
 #define MRT_PB 160  // axis-aligned boxes
@@ -92,6 +97,9 @@ struct SceneCommon {
     const DMeshLeaf* leaf;
     const uint32_t* leaf_idx;
     const DTri* tri;
+    const BvhNode* tbvh;         // triangle BVHs of all meshes (node boxes relative to the instance pos), DMesh::bvh_root
+    const uint32_t* tbvh_ref;    // BVH leaf entries: triangle index within the mesh
+    const DTriLeaf* tri_leaf;    // per triangle: the octree leaves that list it
     uint32_t n_inst, n_lights;
     uint32_t cnt[K_NKIND];    // instances per kind
     uint32_t first[K_NKIND];  // FatInst index of the kind's first instance
@@ -180,6 +188,12 @@ __device__ __forceinline__ float rcp_fixed(float d) {
     return (fabsf(m) == __int_as_float(0x7f800000)) ? (1.0f / MRT_E) : m;
 }
 __device__ __forceinline__ f3 rcp_fixed3(f3 d) { return {rcp_fixed(d.x), rcp_fixed(d.y), rcp_fixed(d.z)}; }
+// The geometrically true slab reciprocal for acceleration-structure nodes, given m = rcp_fixed3(d): a zero
+// component becomes a huge finite slope (inside the slab -> (-huge, +huge), outside -> an empty interval)
+// instead of the reference's 1/E, which belongs to the primitive tests only.
+__device__ __forceinline__ f3 true_rcp3(f3 d, f3 m) {
+    return {d.x == 0.0f ? 1e30f : m.x, d.y == 0.0f ? 1e30f : m.y, d.z == 0.0f ? 1e30f : m.z};
+}
 
 // ------------------------------------------------------------------ RNG: pcg4d counter hash
 // (Jarzynski & Olano, JCGT 2020).  One call = the 4 uniforms of (pixel, sample, block);
@@ -291,6 +305,109 @@ __device__ __forceinline__ bool tri_test(const DTri& tr, f3 o_rel /* ray.orig - 
 // longest lane's candidate list, not for the union of all lanes' leaves (ncu on Mesh.json: the
 // leaf-major loop issued 2/3 of its instructions with <= 3 active lanes).  Candidate order per lane
 // is unchanged (leaf order, then list order), so the first-min / last-max tie rules hold.
+// Triangle-BVH form of the same test (DMesh::bvh_root).  The reference's result only depends on the SET of
+// candidates — every triangle listed by a pierced leaf — and, between equal t, on their order.  So instead of
+// walking every pierced leaf's list (Mesh.json: ~200 leaf slab tests + ~50 triangle tests per ray), a tight BVH
+// over the triangles finds the few triangles the ray actually hits, and each HIT is then checked for candidacy
+// against the handful of octree leaves that list that triangle (DTriLeaf: same slab arithmetic as below, so the
+// holes of the vertex-containment lists, Q15, are reproduced exactly).  Entry = lexicographic minimum of
+// (t, rank of the first pierced occurrence), exit = maximum of (t, rank of the last): the first-min / last-max
+// rules of the sequential walk, independent of the visiting order.  Node boxes are padded on the host so that
+// rounding cannot hide a hit; pruning by the best entry is only allowed when no exit is wanted.
+template <bool ANY, bool WANT_T1>
+__device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh& mh, f3 o_rel, f3 d, f3 m, f3 om,
+                                              float* t0, float* t1, int* i0, int* i1) {
+    const float INF = __int_as_float(0x7f800000);
+    float b0 = INF, b1 = -INF;
+    uint32_t r0 = 0xffffffffu, r1 = 0u;
+    int k0 = -1, k1 = -1;
+    uint32_t stack[32];
+    int sp = 0;
+    uint32_t node = mh.bvh_root;
+    // Two slab tests.  `leaf_slab` is the reference's Box::intersect on an octree leaf, 1/E quirk included
+    // (a zero direction component behaves like a slope of 1/E, so a leaf the ray runs inside of can still be
+    // "missed": part of the candidate rule).  `slab` is for the BVH's own nodes and must be geometrically
+    // true, or a ray running exactly in a mesh's symmetry plane would lose the triangles that end there.
+    auto leaf_slab = [&](float4 lo, float4 hi) -> bool {
+        const float ax = fmaf(lo.x, m.x, -om.x), bx = fmaf(hi.x, m.x, -om.x);
+        const float ay = fmaf(lo.y, m.y, -om.y), by = fmaf(hi.y, m.y, -om.y);
+        const float az = fmaf(lo.z, m.z, -om.z), bz = fmaf(hi.z, m.z, -om.z);
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+        return !(tn > tf || tf < 0.0f);
+    };
+    const f3 mb = true_rcp3(d, m);
+    const f3 omb = o_rel * mb;
+    auto slab = [&](float4 lo, float4 hi, float* tn_out) -> bool {
+        const float ax = fmaf(lo.x, mb.x, -omb.x), bx = fmaf(hi.x, mb.x, -omb.x);
+        const float ay = fmaf(lo.y, mb.y, -omb.y), by = fmaf(hi.y, mb.y, -omb.y);
+        const float az = fmaf(lo.z, mb.z, -omb.z), bz = fmaf(hi.z, mb.z, -omb.z);
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+        *tn_out = tn;
+        return !(tn > tf || tf < 0.0f);
+    };
+    constexpr bool PRUNE = !ANY && !WANT_T1;
+    bool popped = false;
+    for (;;) {
+        const float4 lo = __ldg(&c.tbvh[node].lo), hi = __ldg(&c.tbvh[node].hi);
+        const uint32_t cnt = __float_as_uint(hi.w), first = __float_as_uint(lo.w);
+        bool skip = false;
+        if (PRUNE && popped) {  // a subtree that starts behind the best entry found since it was pushed holds nothing closer
+            float tn;
+            skip = !(slab(lo, hi, &tn) && tn <= b0);
+        }
+        if (!skip && cnt != 0u) {
+            for (uint32_t i = 0; i < cnt; i++) {
+                const uint32_t ti = __ldg(&c.tbvh_ref[first + i]);
+                const DTri* tp = &c.tri[mh.first_tri + ti];
+                DTri tr;
+                tr.v0 = __ldg(&tp->v0); tr.e0 = __ldg(&tp->e0); tr.e1 = __ldg(&tp->e1);
+                float t;
+                if (!tri_test(tr, o_rel, d, &t)) continue;
+                if (PRUNE && !(t <= b0)) continue;  // cannot win: skip the candidacy check
+                // is the triangle a candidate?  first / last pierced leaf that lists it
+                const uint32_t e0 = __float_as_uint(tr.v0.w), en = __float_as_uint(tr.e0.w);
+                uint32_t rf = 0xffffffffu, rl = 0u;
+                bool cand = false;
+                for (uint32_t e = 0; e < en; e++) {
+                    const DTriLeaf tl = c.tri_leaf[e0 + e];
+                    if (!leaf_slab(__ldg(&c.leaf[tl.leaf].lo), __ldg(&c.leaf[tl.leaf].hi))) continue;
+                    if (!cand) rf = tl.rank;
+                    rl = tl.rank;
+                    cand = true;
+                    if (!WANT_T1) break;
+                }
+                if (!cand) continue;
+                if (ANY) return true;
+                if (t < b0 || (t == b0 && rf < r0)) { b0 = t; r0 = rf; k0 = (int)ti; }
+                if (WANT_T1) { if (t > b1 || (t == b1 && rl >= r1)) { b1 = t; r1 = rl; k1 = (int)ti; } }
+            }
+        } else if (!skip) {
+            float tl, tr;
+            bool hl = slab(__ldg(&c.tbvh[first].lo), __ldg(&c.tbvh[first].hi), &tl);
+            bool hr = slab(__ldg(&c.tbvh[first + 1u].lo), __ldg(&c.tbvh[first + 1u].hi), &tr);
+            if (PRUNE) { hl = hl && tl <= b0; hr = hr && tr <= b0; }
+            if (hl && hr) {
+                const bool left_first = tl <= tr;
+                if (sp < 32) stack[sp++] = left_first ? first + 1u : first;
+                node = left_first ? first : first + 1u;
+                popped = false;
+                continue;
+            }
+            if (hl || hr) { node = hl ? first : first + 1u; popped = false; continue; }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+        popped = true;
+    }
+    if (ANY || k0 < 0) return false;
+    *t0 = b0; *i0 = k0;
+    if (WANT_T1) { *t1 = b1; *i1 = k1; } else { *t1 = b0; *i1 = k0; }
+    return true;
+}
+
+template <bool ANY, bool WANT_T1>
 __device__ __forceinline__ bool mesh_test(const SceneCommon& c, uint32_t mesh_id, f3 o_rel, f3 d,
                                           float* t0, float* t1, int* i0, int* i1) {
     const DMesh mh = c.mesh[mesh_id];
@@ -302,6 +419,7 @@ __device__ __forceinline__ bool mesh_test(const SceneCommon& c, uint32_t mesh_id
         const float tf = fminf(fminf(-om.x + ax, -om.y + ay), -om.z + az);
         if (tn > tf || tf < 0.0f) return false;
     }
+    if (mh.bvh_root != 0xffffffffu) return mesh_test_bvh<ANY, WANT_T1>(c, mh, o_rel, d, m, om, t0, t1, i0, i1);
     bool any = false;
     float b0 = 0.f, b1 = 0.f;
     int k0 = -1, k1 = -1;
@@ -418,7 +536,7 @@ __device__ __forceinline__ void best_update(Best& B, bool hit, float t0, float t
     }
 }
 
-struct RayPre { f3 o, d, m, nom, am, nam; };  // m = 1/d (Box::intersect's fix-up applied), nom = -o*m, am = |m|, nam = -|m|
+struct RayPre { f3 o, d, m, nom, am, nam, bm, bnom; };  // m = 1/d (Box::intersect's fix-up applied), nom = -o*m, am = |m|, nam = -|m|; bm, bnom: true_rcp3 form for BVH nodes
 
 // Box::intersect, rt.rs:299-333, centre/half form: n = (o - pos) m, k = half |m|,
 // t0 = max(-n - k), t1 = min(-n + k); miss iff t0 > t1 or t1 < 0.  Two boxes per call, one in
@@ -521,7 +639,7 @@ __device__ __forceinline__ void test_mesh(Best& B, const SceneCommon& c, const R
     if (__float_as_uint(e.b.x) != 0u) { ol = mulXf(x, ol); dl = mulXf(x, r.d); }
     float t0 = 0.0f, t1 = 0.0f;
     int tr0 = -1, tr1 = -1;
-    const bool hit = mesh_test(c, __float_as_uint(e.b.y), ol, dl, &t0, &t1, &tr0, &tr1);
+    const bool hit = mesh_test<ANY, WANT_T1>(c, __float_as_uint(e.b.y), ol, dl, &t0, &t1, &tr0, &tr1);
     best_update<F, ANY, WANT_T1, LE>(B, hit, t0, t1, idx, tr0, tr1);
 }
 
@@ -541,13 +659,24 @@ __device__ __forceinline__ void best_update_lex(Best& B, bool hit, float t0, flo
 }
 // slab interval of an AABB in the ray's parameter, same arithmetic as the primitive box test
 __device__ __forceinline__ bool node_hit(const RayPre& r, float4 lo, float4 hi, float best, float* tn_out) {
+    const float ax = fmaf(lo.x, r.bm.x, r.bnom.x), bx = fmaf(hi.x, r.bm.x, r.bnom.x);
+    const float ay = fmaf(lo.y, r.bm.y, r.bnom.y), by = fmaf(hi.y, r.bm.y, r.bnom.y);
+    const float az = fmaf(lo.z, r.bm.z, r.bnom.z), bz = fmaf(hi.z, r.bm.z, r.bnom.z);
+    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    *tn_out = tn;
+    return tn <= tf && tf >= 0.0f && tn <= best;  // '<=': an equal t0 with a lower index must still be found
+}
+// The same interval with the primitive boxes' own arithmetic (r.m: the 1/E quirk included).  For a bracket
+// around AXIS-ALIGNED BOXES ONLY this is exactly monotone — every box interval computed with the same
+// formula lies inside its bracket's — so the specialised kernel's cluster brackets use this cheaper form.
+__device__ __forceinline__ bool bracket_hit(const RayPre& r, float4 lo, float4 hi, float best) {
     const float ax = fmaf(lo.x, r.m.x, r.nom.x), bx = fmaf(hi.x, r.m.x, r.nom.x);
     const float ay = fmaf(lo.y, r.m.y, r.nom.y), by = fmaf(hi.y, r.m.y, r.nom.y);
     const float az = fmaf(lo.z, r.m.z, r.nom.z), bz = fmaf(hi.z, r.m.z, r.nom.z);
     const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
     const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-    *tn_out = tn;
-    return tn <= tf && tf >= 0.0f && tn <= best;  // '<=': an equal t0 with a lower index must still be found
+    return tn <= tf && tf >= 0.0f && tn <= best;
 }
 template <uint32_t F, bool ANY, bool WANT_T1>
 __device__ __forceinline__ void bvh_leaf(Best& B, const GlobalScene& s, const RayPre& r, const RayPk& rp, uint32_t ref) {
@@ -582,7 +711,7 @@ __device__ __forceinline__ void bvh_leaf(Best& B, const GlobalScene& s, const Ra
             const SlimInst e = ldg_slim(s.mesh + k);
             f3 ol = r.o - xyz(e.a), dl = r.d;
             if (__float_as_uint(e.b.x) != 0u) { ol = mulXf(s.mesh_m[k], ol); dl = mulXf(s.mesh_m[k], r.d); }
-            hit = mesh_test(c, __float_as_uint(e.b.y), ol, dl, &t0, &t1, &tr0, &tr1);
+            hit = mesh_test<ANY, WANT_T1>(c, __float_as_uint(e.b.y), ol, dl, &t0, &t1, &tr0, &tr1);
             best_update_lex<F, ANY, WANT_T1>(B, hit, t0, t1, (int)(c.first[K_MESH] + k), tr0, tr1);
         }
     }
@@ -647,6 +776,8 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
     r.nom = mk(-o.x * r.m.x, -o.y * r.m.y, -o.z * r.m.z);
     r.am = mk(fabsf(r.m.x), fabsf(r.m.y), fabsf(r.m.z));
     r.nam = -r.am;
+    r.bm = true_rcp3(d, r.m);  // only the node tests (scene BVH, cluster brackets) read these
+    r.bnom = mk(-o.x * r.bm.x, -o.y * r.bm.y, -o.z * r.bm.z);
     const RayPk rp = {pk2(o.x, d.x), pk2(o.y, d.y), pk2(o.z, d.z)};
     Best B;
     B.t0 = __int_as_float(0x7f800000); B.t1 = 0.0f; B.bi = -1; B.tr0 = B.tr1 = -1; B.any = false;
@@ -672,7 +803,7 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
         test_mesh<F, ANY, WANT_T1, false>(B, c, r, SlimInst{make_float4(px, py, pz, 0.0f), make_float4(__uint_as_float(rot), __uint_as_float(mid), 0.0f, 0.0f)}, x__, (int)(MRT_JIT_FIRST_MESH + (k))); }
         // J_CB / J_CE bracket a cluster of consecutive boxes with its bounding box (big scenes only): the
         // cluster is skipped when the ray misses the box or enters it behind the best hit so far
-#define J_CB(lx, ly, lz, hx, hy, hz) { float tn__; if (node_hit(r, make_float4(lx, ly, lz, 0.0f), make_float4(hx, hy, hz, 0.0f), ANY ? __int_as_float(0x7f800000) : B.t0, &tn__)) {
+#define J_CB(lx, ly, lz, hx, hy, hz) { if (bracket_hit(r, make_float4(lx, ly, lz, 0.0f), make_float4(hx, hy, hz, 0.0f), ANY ? __int_as_float(0x7f800000) : B.t0)) {
 #define J_CE }}
         MRT_JIT_BOXPAIRS(J_BOXP, J_BOXS, J_BOX1, J_CB, J_CE)
 #undef J_CB

@@ -376,6 +376,53 @@ def test_scene_bvh_returns_the_brute_force_hits(seed, monkeypatch):
     assert ok[fin].mean() >= 0.93
 
 
+def _mesh_scene(seed):
+    """A scene of random meshes (big and small triangles, so that the vertex-containment holes of the
+    octree lists are hit), one of them transparent (exit hits wanted), instanced with rotations, plus a light
+    (shadow rays: any-hit queries)."""
+    from micro_raytracer_b200.scene import render_from_dict
+    rng = np.random.default_rng(1000 + seed)
+    objs = []
+    for k in range(3):
+        n = int(rng.integers(20, 300))
+        c = rng.uniform(-0.4, 0.4, (n, 1, 3))
+        size = rng.choice([0.03, 0.1, 0.4], (n, 1, 1), p=[0.5, 0.3, 0.2])
+        tris = (c + rng.uniform(-1, 1, (n, 3, 3)) * size).round(4)
+        mat = {"rough": float(rng.uniform(0, 1)), "albedo": rng.uniform(0.2, 1, 3).round(3).tolist()}
+        if k == 1 and seed % 2 == 0:
+            mat.update({"opacity": 0.3, "glass": 0.1})
+        inst = [[rng.uniform(-0.8, 0.8, 3).round(3).tolist(), [float(rng.uniform(-0.5, 0.5)), *rng.normal(size=3).round(3).tolist()]] for _ in range(2)]
+        objs.append({"type": "mesh", "mesh": tris.tolist(), "mat": mat, "inst": inst})
+    objs.append({"type": "plane", "n": [0, 0, 1], "pos": [0, 0, -1], "mat": {"rough": 1}})
+    d = {"rt": {"bounce": 4}, "frame": {"res": [96, 64], "cam": {"pos": [0, -2.5, 0.2], "fov": 60}},
+         "scene": {"renderer": objs, "light": [{"type": "point", "pos": [0.5, -1, 1.5]}], "sky": {"color": [0.3, 0.4, 0.5], "pwr": 0.5}}}
+    return render_from_dict(d)
+
+
+@pytest.mark.parametrize("name", ["Mesh", *[f"random{k}" for k in range(int(os.environ.get("MRT_FUZZ_MESH_SEEDS", "6")))]])
+@pytest.mark.parametrize("jit", [0, 2], ids=["generic", "jit"])  # MRT_JIT_OFF, MRT_JIT_FORCE
+def test_triangle_bvh_returns_the_leaf_walk_hits(name, jit, monkeypatch):
+    """Meshes are searched through a BVH over their triangles; a hit only counts if one of the octree
+    leaves that list the triangle is pierced (the reference's candidate set, rt.rs:707-772).  Hit ids,
+    t0, t1, triangle ids and the accumulated radiance must equal the sequential leaf walk's BIT FOR BIT."""
+    r = load("Mesh", res=(96, 54)) if name == "Mesh" else _mesh_scene(int(name[6:]))
+    res = {}
+    for mode in ("bvh", "walk"):
+        if mode == "walk":
+            monkeypatch.setenv("MRT_NO_MESH_BVH", "1")
+        s = mrt.Sampler(device=0)
+        s.set_option(2, jit)
+        s.execute(r.scene, r.frame, r.rt, 3)
+        res[mode] = (s.trace_primary(), s.accum()[0])
+    hb, ab = res["bvh"]
+    h0, a0 = res["walk"]
+    assert (hb["tri0"] >= 0).mean() > 0.02
+    for f in ("obj", "inst", "tri0", "tri1"):
+        assert (hb[f] == h0[f]).all(), f
+    assert (hb["t0"] == h0["t0"]).all() and (hb["t1"] == h0["t1"]).all()
+    assert np.array_equal(ab, a0)
+
+
 def test_full_size_film_properties():
     """Size-independent properties at the headline film size (2160x2160), per kernel: a render is
     bit-reproducible and does not depend on how the passes are cut into calls or launches (the RNG is
