@@ -291,6 +291,17 @@ def main():
                 line["roofline"]["traffic"] = json.load(open(prof)).get("path_kernel_bytes_per_launch")
             except Exception:  # noqa: BLE001
                 pass
+        # the other candidate bound, to show it is not the one: HBM traffic of the same launch
+        # (algorithmic = one float4 read + one float4 write per supersampled pixel per launch)
+        hbm_peak, hbm_src = 6534.1, "fallback: B200_PROFILING.md"
+        try:
+            hbm_peak, hbm_src = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
+        except Exception:  # noqa: BLE001
+            pass
+        hbm_bytes = nw * nh * 16 * 2
+        hbm_gbs = hbm_bytes / (launch_ms * 1e-3) / 1e9
+        line["roofline"]["hbm"] = {"algorithmic_bytes_per_launch": hbm_bytes, "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                   "frac": hbm_gbs / hbm_peak, "peak_source": hbm_src}
         if not args.no_cpu_baseline and n_gpus == 1:
             line["cpu_baseline"] = cpu_baseline(args, r, nw, nh)
         print(json.dumps(line), flush=True)

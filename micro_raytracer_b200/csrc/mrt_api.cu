@@ -99,7 +99,6 @@ struct mrt_ctx {
     DevBuf<Xf> d_mesh_m;
     DevBuf<BoxPair> d_boxp;
     DevBuf<BvhNode> d_bvh;
-    DevBuf<uint32_t> d_bvh_ref;
     DevBuf<BxfInst> d_bxf;
     DevBuf<FatInst> d_fat;
     DevBuf<DTex> d_tex;
@@ -109,7 +108,6 @@ struct mrt_ctx {
     DevBuf<uint32_t> d_leaf_idx;
     DevBuf<DTri> d_tri;
     DevBuf<BvhNode> d_tbvh;          // triangle BVHs of the meshes
-    DevBuf<uint32_t> d_tbvh_ref;
     DevBuf<DTriLeaf> d_tri_leaf;     // per triangle: the octree leaves that list it
     DevBuf<uint32_t> d_obj_inst;
 
@@ -238,24 +236,20 @@ bool all_finite(const float* v, int n) {
     return true;
 }
 
-// ---- scene-level BVH over the finite instances (mrt_device.cuh: BvhNode): median split of the
-// centroids along the widest axis, one reference per leaf (measured best), children adjacent.
+// ---- BVH builder (scene-level BVH over the finite instances, triangle BVHs of the meshes; mrt_device.cuh:
+// BvhNode): median split of the centroids along the widest axis, one primitive per leaf (measured best).
 struct PrimBox { float lo[3], hi[3]; uint32_t ref; };
-void bvh_build(std::vector<PrimBox>& prims, size_t begin, size_t end, size_t node, std::vector<BvhNode>* nodes, std::vector<uint32_t>* refs, size_t leaf_max) {
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+// Returns the reference of the subtree over prims[begin, end): a leaf (MRT_BVH_LEAF | prims[begin].ref) for a
+// single primitive, else the index of a node that holds the boxes and references of its two halves.
+uint32_t bvh_build(std::vector<PrimBox>& prims, size_t begin, size_t end, std::vector<BvhNode>* nodes, int depth = 0, int* max_depth = nullptr) {
+    if (max_depth) *max_depth = std::max(*max_depth, depth);
+    if (end - begin == 1) return MRT_BVH_LEAF | prims[begin].ref;
     float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (size_t i = begin; i < end; i++)
         for (int a = 0; a < 3; a++) {
-            lo[a] = std::fmin(lo[a], prims[i].lo[a]); hi[a] = std::fmax(hi[a], prims[i].hi[a]);
             const float cc = 0.5f * (prims[i].lo[a] + prims[i].hi[a]);
             clo[a] = std::fmin(clo[a], cc); chi[a] = std::fmax(chi[a], cc);
         }
-    if (end - begin <= leaf_max) {
-        (*nodes)[node].lo = make_float4(lo[0], lo[1], lo[2], u2f((uint32_t)refs->size()));
-        (*nodes)[node].hi = make_float4(hi[0], hi[1], hi[2], u2f((uint32_t)(end - begin)));
-        for (size_t i = begin; i < end; i++) refs->push_back(prims[i].ref);
-        return;
-    }
     int ax = 0;
     if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
     if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
@@ -263,12 +257,22 @@ void bvh_build(std::vector<PrimBox>& prims, size_t begin, size_t end, size_t nod
     std::nth_element(prims.begin() + begin, prims.begin() + mid, prims.begin() + end, [ax](const PrimBox& a, const PrimBox& b) {
         return a.lo[ax] + a.hi[ax] < b.lo[ax] + b.hi[ax];
     });
-    const size_t left = nodes->size();
-    nodes->resize(left + 2);
-    (*nodes)[node].lo = make_float4(lo[0], lo[1], lo[2], u2f((uint32_t)left));
-    (*nodes)[node].hi = make_float4(hi[0], hi[1], hi[2], u2f(0u));
-    bvh_build(prims, begin, mid, left, nodes, refs, leaf_max);
-    bvh_build(prims, mid, end, left + 1, nodes, refs, leaf_max);
+    auto bounds = [&](size_t b0, size_t e0, float* lo, float* hi) {
+        for (int a = 0; a < 3; a++) { lo[a] = INFINITY; hi[a] = -INFINITY; }
+        for (size_t i = b0; i < e0; i++)
+            for (int a = 0; a < 3; a++) { lo[a] = std::fmin(lo[a], prims[i].lo[a]); hi[a] = std::fmax(hi[a], prims[i].hi[a]); }
+    };
+    const size_t node = nodes->size();
+    nodes->emplace_back();
+    float llo[3], lhi[3], rlo[3], rhi[3];
+    bounds(begin, mid, llo, lhi);
+    bounds(mid, end, rlo, rhi);
+    const uint32_t l = bvh_build(prims, begin, mid, nodes, depth + 1, max_depth);
+    const uint32_t r = bvh_build(prims, mid, end, nodes, depth + 1, max_depth);
+    BvhNode& n = (*nodes)[node];
+    n.llo = make_float4(llo[0], llo[1], llo[2], u2f(l)); n.lhi = make_float4(lhi[0], lhi[1], lhi[2], 0.0f);
+    n.rlo = make_float4(rlo[0], rlo[1], rlo[2], u2f(r)); n.rhi = make_float4(rhi[0], rhi[1], rhi[2], 0.0f);
+    return (uint32_t)node;
 }
 // world-space AABB of an object-space box of half extents h centred on pos, under world->object matrix M
 // (object->world is M^T), padded so that rounding in the primitive tests cannot leave the node
@@ -335,8 +339,8 @@ void mrt_destroy(mrt_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->jit_requested && !c->jit_header.empty()) mrt_jit_wait(c->jit_header);
     for (auto& b : c->d_slim) b.release();
-    c->d_boxp.release(); c->d_bvh.release(); c->d_bvh_ref.release(); c->d_bxf.release(); c->d_mesh_m.release(); c->d_fat.release(); c->d_tex.release(); c->d_texels.release();
-    c->d_mesh.release(); c->d_leaf.release(); c->d_leaf_idx.release(); c->d_tri.release(); c->d_tbvh.release(); c->d_tbvh_ref.release(); c->d_tri_leaf.release(); c->d_obj_inst.release();
+    c->d_boxp.release(); c->d_bvh.release(); c->d_bxf.release(); c->d_mesh_m.release(); c->d_fat.release(); c->d_tex.release(); c->d_texels.release();
+    c->d_mesh.release(); c->d_leaf.release(); c->d_leaf_idx.release(); c->d_tri.release(); c->d_tbvh.release(); c->d_tri_leaf.release(); c->d_obj_inst.release();
     c->d_accum.release(); c->d_ss.release(); c->d_out.release(); c->d_tmp.release(); c->d_rgb.release();
     c->d_wv.release(); c->d_wh.release(); c->d_lv.release(); c->d_cv.release(); c->d_lh.release(); c->d_ch.release();
     c->d_hits.release();
@@ -385,10 +389,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     std::vector<uint32_t> leaf_idx;
     std::vector<DTri> tris;
     std::vector<BvhNode> tbvh;
-    std::vector<uint32_t> tbvh_ref;
     std::vector<DTriLeaf> tri_leaf;
-    size_t tbvh_leaf = 1;  // triangles per BVH leaf: 1 measured best (Mesh.json 1418 vs 1377 Mpaths/s with 2, 1247 with 4)
-    if (const char* e = std::getenv("MRT_MESH_BVH_LEAF")) tbvh_leaf = (size_t)std::max(1, std::atoi(e));  // experiment knob
     const bool mesh_bvh = !std::getenv("MRT_NO_MESH_BVH");  // test knob: the sequential leaf walk instead
     for (uint32_t i = 0; i < s->n_meshes; i++) {
         const mrt_mesh& m = s->meshes[i];
@@ -446,10 +447,11 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
                 pb.push_back(b);
             }
             if (finite && !pb.empty()) {
-                const size_t root = tbvh.size();
-                tbvh.resize(root + 1);
-                bvh_build(pb, 0, pb.size(), root, &tbvh, &tbvh_ref, tbvh_leaf);
-                meshes[i].bvh_root = (uint32_t)root;
+                const size_t mark = tbvh.size();
+                int depth = 0;
+                const uint32_t root = bvh_build(pb, 0, pb.size(), &tbvh, 0, &depth);
+                if (depth <= 30) meshes[i].bvh_root = root;  // the traversal stack holds 32 entries
+                else tbvh.resize(mark);
             }
         }
     }
@@ -587,18 +589,16 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     CK(c->d_bxf.upload(bxf));
     // scene-level BVH: only for scenes too large to unroll (the specialised kernel covers <= 128 primitives)
     std::vector<BvhNode> bvh_nodes;
-    std::vector<uint32_t> bvh_refs;
+    uint32_t bvh_root = 0;
     size_t bvh_min = 128;  // the specialised (unrolled) kernel covers up to 128 primitives
     if (const char* e = std::getenv("MRT_BVH_MIN")) bvh_min = (size_t)std::max(0, std::atoi(e));  // experiment knob
-    const bool use_bvh = prim_boxes.size() > bvh_min && prim_boxes_ok && prim_boxes.size() < (1u << 28) && !std::getenv("MRT_NO_BVH");
+    bool use_bvh = prim_boxes.size() > bvh_min && prim_boxes_ok && prim_boxes.size() < (1u << 28) && !std::getenv("MRT_NO_BVH");
     if (use_bvh) {
-        bvh_nodes.resize(1);
-        size_t leaf_max = 1;  // measured on Instance.json: 1 -> 851, 2 -> 823, 4 -> 750, 8 -> 649 Mpaths/s
-        if (const char* e = std::getenv("MRT_BVH_LEAF")) leaf_max = (size_t)std::max(1, std::atoi(e));  // experiment knob
-        bvh_build(prim_boxes, 0, prim_boxes.size(), 0, &bvh_nodes, &bvh_refs, leaf_max);
+        int depth = 0;
+        bvh_root = bvh_build(prim_boxes, 0, prim_boxes.size(), &bvh_nodes, 0, &depth);
+        if (depth > 30) use_bvh = false;  // the traversal stack holds 32 entries (median splits: never for < 2^28 primitives)
     }
     CK(c->d_bvh.upload(bvh_nodes));
-    CK(c->d_bvh_ref.upload(bvh_refs));
     CK(c->d_mesh_m.upload(mesh_m));
     CK(c->d_fat.upload(fat));
     CK(c->d_tex.upload(tex));
@@ -608,7 +608,6 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     CK(c->d_leaf_idx.upload(leaf_idx));
     CK(c->d_tri.upload(tris));
     CK(c->d_tbvh.upload(tbvh));
-    CK(c->d_tbvh_ref.upload(tbvh_ref));
     CK(c->d_tri_leaf.upload(tri_leaf));
     CK(c->d_obj_inst.upload(obj_inst));
 
@@ -734,7 +733,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     SceneCommon sc{};
     sc.fat = c->d_fat.p; sc.tex = c->d_tex.p; sc.texels = c->d_texels.p;
     sc.mesh = c->d_mesh.p; sc.leaf = c->d_leaf.p; sc.leaf_idx = c->d_leaf_idx.p; sc.tri = c->d_tri.p;
-    sc.tbvh = c->d_tbvh.p; sc.tbvh_ref = c->d_tbvh_ref.p; sc.tri_leaf = c->d_tri_leaf.p;
+    sc.tbvh = c->d_tbvh.p; sc.tri_leaf = c->d_tri_leaf.p;
     sc.n_inst = (uint32_t)fat.size();
     sc.n_lights = s->n_lights;
     for (uint32_t k = 0; k < K_NKIND; k++) { sc.first[k] = first[k]; sc.cnt[k] = cnt[k]; }
@@ -751,7 +750,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     c->gscene.boxp = c->d_boxp.p; c->gscene.sph = c->d_slim[K_SPHERE].p; c->gscene.pln = c->d_slim[K_PLANE].p;
     c->gscene.bxf = c->d_bxf.p;
     c->gscene.bvh = use_bvh ? c->d_bvh.p : nullptr;
-    c->gscene.bvh_ref = c->d_bvh_ref.p;
+    c->gscene.bvh_root = bvh_root;
     c->gscene.mesh = c->d_slim[K_MESH].p; c->gscene.mesh_m = c->d_mesh_m.p;
     c->in_param = cnt[K_BOX] <= MRT_PB && cnt[K_SPHERE] <= MRT_PS && cnt[K_PLANE] <= MRT_PP && cnt[K_BOX_XF] <= MRT_PX &&
                   cnt[K_MESH] <= MRT_PM && !use_bvh && !std::getenv("MRT_FORCE_GLOBAL_SCENE");

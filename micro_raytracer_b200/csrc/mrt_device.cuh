@@ -69,7 +69,12 @@ static_assert(sizeof(FatInst) == 128, "FatInst must be one cache line");
 // (> 128 primitives).  It only narrows the candidate set: every candidate runs the same
 // primitive test as the brute-force loop and the winner is the lexicographic minimum of (t0, instance
 // index), i.e. exactly the brute-force result.  Children of an inner node are adjacent.
-struct BvhNode { float4 lo, hi; };  // lo.w = bits: left child (inner) / first ref (leaf); hi.w = bits: 0 (inner) / ref count (leaf)
+// A node holds the boxes of BOTH its children, so one visit is one round of loads (the node's own box was
+// tested at its parent); llo.w / rlo.w (bits) = child reference: bit 31 set = leaf, the low bits are the
+// primitive (scene BVH: kind << 28 | index within the kind's table; mesh BVH: triangle index within the
+// mesh), else the index of the child node.  One primitive per leaf, so leaves need no node at all.
+struct BvhNode { float4 llo, lhi, rlo, rhi; };
+#define MRT_BVH_LEAF 0x80000000u
 struct DLight { float4 v_kind; float4 color_pwr; };  // v.xyz (pos or unit -dir), w = kind bits ; color.rgb, pwr
 struct DTex { uint32_t w, h, first, has_dat; };      // texel offset into the float4 texel array
 struct DMeshLeaf { float4 lo, hi; };                  // leaf box relative to instance pos; lo.w = first index (bits), hi.w = count (bits)
@@ -97,8 +102,7 @@ struct SceneCommon {
     const DMeshLeaf* leaf;
     const uint32_t* leaf_idx;
     const DTri* tri;
-    const BvhNode* tbvh;         // triangle BVHs of all meshes (node boxes relative to the instance pos), DMesh::bvh_root
-    const uint32_t* tbvh_ref;    // BVH leaf entries: triangle index within the mesh
+    const BvhNode* tbvh;         // triangle BVHs of all meshes (boxes relative to the instance pos); root reference in DMesh::bvh_root
     const DTriLeaf* tri_leaf;    // per triangle: the octree leaves that list it
     uint32_t n_inst, n_lights;
     uint32_t cnt[K_NKIND];    // instances per kind
@@ -126,7 +130,7 @@ struct GlobalScene {
     const SlimInst* mesh;
     const Xf* mesh_m;
     const BvhNode* bvh;        // nullptr: brute force
-    const uint32_t* bvh_ref;   // leaf entries: kind << 28 | index within the kind's table
+    uint32_t bvh_root;         // reference of the root (a leaf when the scene has one finite instance)
 };
 
 struct FilmParams {
@@ -322,8 +326,8 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
     uint32_t r0 = 0xffffffffu, r1 = 0u;
     int k0 = -1, k1 = -1;
     uint32_t stack[32];
+    float stack_t[32];  // entry parameter of the pushed subtree's box
     int sp = 0;
-    uint32_t node = mh.bvh_root;
     // Two slab tests.  `leaf_slab` is the reference's Box::intersect on an octree leaf, 1/E quirk included
     // (a zero direction component behaves like a slope of 1/E, so a leaf the ray runs inside of can still be
     // "missed": part of the candidate rule).  `slab` is for the BVH's own nodes and must be geometrically
@@ -348,24 +352,15 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
         return !(tn > tf || tf < 0.0f);
     };
     constexpr bool PRUNE = !ANY && !WANT_T1;
-    bool popped = false;
+    uint32_t cur = mh.bvh_root;
     for (;;) {
-        const float4 lo = __ldg(&c.tbvh[node].lo), hi = __ldg(&c.tbvh[node].hi);
-        const uint32_t cnt = __float_as_uint(hi.w), first = __float_as_uint(lo.w);
-        bool skip = false;
-        if (PRUNE && popped) {  // a subtree that starts behind the best entry found since it was pushed holds nothing closer
-            float tn;
-            skip = !(slab(lo, hi, &tn) && tn <= b0);
-        }
-        if (!skip && cnt != 0u) {
-            for (uint32_t i = 0; i < cnt; i++) {
-                const uint32_t ti = __ldg(&c.tbvh_ref[first + i]);
-                const DTri* tp = &c.tri[mh.first_tri + ti];
-                DTri tr;
-                tr.v0 = __ldg(&tp->v0); tr.e0 = __ldg(&tp->e0); tr.e1 = __ldg(&tp->e1);
-                float t;
-                if (!tri_test(tr, o_rel, d, &t)) continue;
-                if (PRUNE && !(t <= b0)) continue;  // cannot win: skip the candidacy check
+        if (cur & MRT_BVH_LEAF) {
+            const uint32_t ti = cur & ~MRT_BVH_LEAF;
+            const DTri* tp = &c.tri[mh.first_tri + ti];
+            DTri tr;
+            tr.v0 = __ldg(&tp->v0); tr.e0 = __ldg(&tp->e0); tr.e1 = __ldg(&tp->e1);
+            float t;
+            if (tri_test(tr, o_rel, d, &t) && !(PRUNE && !(t <= b0))) {
                 // is the triangle a candidate?  first / last pierced leaf that lists it
                 const uint32_t e0 = __float_as_uint(tr.v0.w), en = __float_as_uint(tr.e0.w);
                 uint32_t rf = 0xffffffffu, rl = 0u;
@@ -378,28 +373,34 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
                     cand = true;
                     if (!WANT_T1) break;
                 }
-                if (!cand) continue;
-                if (ANY) return true;
-                if (t < b0 || (t == b0 && rf < r0)) { b0 = t; r0 = rf; k0 = (int)ti; }
-                if (WANT_T1) { if (t > b1 || (t == b1 && rl >= r1)) { b1 = t; r1 = rl; k1 = (int)ti; } }
+                if (cand) {
+                    if (ANY) return true;
+                    if (t < b0 || (t == b0 && rf < r0)) { b0 = t; r0 = rf; k0 = (int)ti; }
+                    if (WANT_T1) { if (t > b1 || (t == b1 && rl >= r1)) { b1 = t; r1 = rl; k1 = (int)ti; } }
+                }
             }
-        } else if (!skip) {
+        } else {
+            const float4 llo = __ldg(&c.tbvh[cur].llo), lhi = __ldg(&c.tbvh[cur].lhi);
+            const float4 rlo = __ldg(&c.tbvh[cur].rlo), rhi = __ldg(&c.tbvh[cur].rhi);
             float tl, tr;
-            bool hl = slab(__ldg(&c.tbvh[first].lo), __ldg(&c.tbvh[first].hi), &tl);
-            bool hr = slab(__ldg(&c.tbvh[first + 1u].lo), __ldg(&c.tbvh[first + 1u].hi), &tr);
+            bool hl = slab(llo, lhi, &tl), hr = slab(rlo, rhi, &tr);
             if (PRUNE) { hl = hl && tl <= b0; hr = hr && tr <= b0; }
+            const uint32_t cl = __float_as_uint(llo.w), cr = __float_as_uint(rlo.w);
             if (hl && hr) {
                 const bool left_first = tl <= tr;
-                if (sp < 32) stack[sp++] = left_first ? first + 1u : first;
-                node = left_first ? first : first + 1u;
-                popped = false;
+                if (sp < 32) { stack[sp] = left_first ? cr : cl; stack_t[sp] = left_first ? tr : tl; sp++; }
+                cur = left_first ? cl : cr;
                 continue;
             }
-            if (hl || hr) { node = hl ? first : first + 1u; popped = false; continue; }
+            if (hl || hr) { cur = hl ? cl : cr; continue; }
         }
-        if (sp == 0) break;
-        node = stack[--sp];
-        popped = true;
+        // next subtree; one that starts behind the best entry found since it was pushed holds nothing closer
+        bool more = false;
+        while (sp > 0) {
+            --sp;
+            if (!PRUNE || stack_t[sp] <= b0) { cur = stack[sp]; more = true; break; }
+        }
+        if (!more) break;
     }
     if (ANY || k0 < 0) return false;
     *t0 = b0; *i0 = k0;
@@ -719,32 +720,36 @@ __device__ __forceinline__ void bvh_leaf(Best& B, const GlobalScene& s, const Ra
 template <uint32_t F, bool ANY, bool WANT_T1>
 __device__ __forceinline__ void bvh_traverse(Best& B, const GlobalScene& s, const RayPre& r, const RayPk& rp) {
     uint32_t stack[32];
+    float stack_t[32];  // entry parameter of the pushed subtree's box
     int sp = 0;
-    uint32_t node = 0;
-    {
-        float tn;
-        if (!node_hit(r, __ldg(&s.bvh[0].lo), __ldg(&s.bvh[0].hi), B.t0, &tn)) return;
-    }
+    uint32_t cur = s.bvh_root;
     for (;;) {
-        const float4 lo = __ldg(&s.bvh[node].lo), hi = __ldg(&s.bvh[node].hi);
-        const uint32_t cnt = __float_as_uint(hi.w), first = __float_as_uint(lo.w);
-        if (cnt != 0u) {
-            for (uint32_t i = 0; i < cnt; i++) bvh_leaf<F, ANY, WANT_T1>(B, s, r, rp, __ldg(&s.bvh_ref[first + i]));
+        if (cur & MRT_BVH_LEAF) {
+            bvh_leaf<F, ANY, WANT_T1>(B, s, r, rp, cur & ~MRT_BVH_LEAF);
             if constexpr (ANY) { if (B.any) return; }
         } else {
+            const float4 llo = __ldg(&s.bvh[cur].llo), lhi = __ldg(&s.bvh[cur].lhi);
+            const float4 rlo = __ldg(&s.bvh[cur].rlo), rhi = __ldg(&s.bvh[cur].rhi);
             float tl, tr;
-            const bool hl = node_hit(r, __ldg(&s.bvh[first].lo), __ldg(&s.bvh[first].hi), B.t0, &tl);
-            const bool hr = node_hit(r, __ldg(&s.bvh[first + 1u].lo), __ldg(&s.bvh[first + 1u].hi), B.t0, &tr);
+            const bool hl = node_hit(r, llo, lhi, B.t0, &tl);
+            const bool hr = node_hit(r, rlo, rhi, B.t0, &tr);
+            const uint32_t cl = __float_as_uint(llo.w), cr = __float_as_uint(rlo.w);
             if (hl && hr) {
                 const bool left_first = tl <= tr;
-                if (sp < 32) stack[sp++] = left_first ? first + 1u : first;
-                node = left_first ? first : first + 1u;
+                if (sp < 32) { stack[sp] = left_first ? cr : cl; stack_t[sp] = left_first ? tr : tl; sp++; }
+                cur = left_first ? cl : cr;
                 continue;
             }
-            if (hl || hr) { node = hl ? first : first + 1u; continue; }
+            if (hl || hr) { cur = hl ? cl : cr; continue; }
         }
-        if (sp == 0) return;
-        node = stack[--sp];
+        // next subtree; one that starts behind the best hit found since it was pushed holds nothing closer
+        // ('<=': an equal t0 with a lower index must still be found)
+        bool more = false;
+        while (sp > 0) {
+            --sp;
+            if (ANY || stack_t[sp] <= B.t0) { cur = stack[sp]; more = true; break; }
+        }
+        if (!more) return;
     }
 }
 
