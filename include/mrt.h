@@ -141,6 +141,9 @@ int mrt_create(mrt_ctx** out, int device, uint32_t workers, uint32_t n_dim);
 void mrt_destroy(mrt_ctx* ctx);
 const char* mrt_last_error(const mrt_ctx* ctx);   /* ctx may be NULL: last create error */
 int mrt_abi_version(void);
+/* Number of usable CUDA devices (0 and MRT_ERR_CUDA without a driver): what a multi-GPU host
+ * (one context per device + mrt_set_partition, see below) may pass to mrt_create. */
+int mrt_device_count(int* n);
 
 /* The three borrows of Sampler::execute (sampler.rs:28).  Data is validated, packed
  * into the device layout and uploaded.  Changing scene or frame drops the accumulated

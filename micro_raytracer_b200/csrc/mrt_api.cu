@@ -298,6 +298,15 @@ int mrt_abi_version(void) { return MRT_ABI_VERSION; }
 
 const char* mrt_last_error(const mrt_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
 
+int mrt_device_count(int* n) {
+    if (!n) return MRT_ERR_INVALID;
+    *n = 0;
+    int k = 0;
+    if (cudaGetDeviceCount(&k) != cudaSuccess) { cudaGetLastError(); return MRT_ERR_CUDA; }
+    *n = k;
+    return MRT_OK;
+}
+
 int mrt_create(mrt_ctx** out, int device, uint32_t workers, uint32_t n_dim) {
     (void)workers; (void)n_dim;  // --worker / --dim: the CUDA grid replaces the tile pool
     if (!out) { g_create_err = "mrt_create: null out"; return MRT_ERR_INVALID; }

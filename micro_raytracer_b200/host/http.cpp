@@ -109,7 +109,7 @@ static void handle(int fd, int device, const Logger& log) {
 }
 
 // HttpServer::start, http.rs:150-162: accept forever, one thread per connection
-void serve(const std::string& address, int device, const Logger& log) {
+void serve(const std::string& address, int device, int n_gpus, const Logger& log) {
     const size_t c = address.rfind(':');
     std::string host = c == std::string::npos ? "localhost" : address.substr(0, c);
     const std::string port = c == std::string::npos ? address : address.substr(c + 1);
@@ -128,11 +128,13 @@ void serve(const std::string& address, int device, const Logger& log) {
     }
     freeaddrinfo(res);
     if (log) log("http:listening: " + address);
+    unsigned n_conn = 0;
     for (;;) {
         const int fd = ::accept(srv, nullptr, nullptr);
         if (fd < 0) continue;
-        std::thread([fd, device, log]() {
-            try { handle(fd, device, log); } catch (const std::exception& e) { if (log) log(std::string("http: ") + e.what()); }
+        const int dev = device + (int)(n_conn++ % (unsigned)(n_gpus > 0 ? n_gpus : 1));  // one Sampler per request, GPUs in turn
+        std::thread([fd, dev, log]() {
+            try { handle(fd, dev, log); } catch (const std::exception& e) { if (log) log(std::string("http: ") + e.what()); }
             ::shutdown(fd, SHUT_RDWR);
             ::close(fd);
         }).detach();

@@ -475,6 +475,8 @@ std::string usage() {
            "      --light ...        point: <f32 x3> | dir: <f32 x3>  pwr: col:\n"
            "      --sky r g b pwr    Scene sky color\n"
            "      --device N         CUDA device (extension)\n"
+           "      --gpus N           render on N GPUs, devices N.. from --device: sample split + one NCCL reduce (extension);\n"
+           "                         with --http: requests go round-robin over the N GPUs\n"
            "      --seed N           RNG seed (extension: the reference is unseedable)\n";
 }
 
@@ -530,6 +532,7 @@ CliArgs parse_cli(const std::vector<std::string>& argv) {
         else if (f == "--light") many(a.light);
         else if (f == "--sky") { many(a.sky); if (a.sky->empty()) throw Error("a value is required for '--sky' but none was supplied"); }
         else if (f == "--device") a.device = (int)integer(f);
+        else if (f == "--gpus") { a.gpus = (int)integer(f); if (a.gpus < 1) throw Error("invalid value for '--gpus': at least 1"); }
         else if (f == "--seed") a.seed = (uint64_t)std::strtoull(one(f).c_str(), nullptr, 0);
         else if (f == "--dump-packed") a.dump_packed = one(f);
         else if (f == "-h" || f == "--help") throw Error(usage());

@@ -31,6 +31,7 @@ struct CliArgs {
     std::optional<std::vector<long>> res;
     std::optional<std::vector<std::string>> cam, obj, light, sky;
     int device = 0;
+    int gpus = 1;          // --gpus N (extension): devices device .. device+N-1 render one image together
     uint64_t seed = 0x5EED;
 };
 CliArgs parse_cli(const std::vector<std::string>& argv);

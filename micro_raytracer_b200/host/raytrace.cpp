@@ -9,6 +9,7 @@
 
 #include "http.hpp"
 #include "image_io.hpp"
+#include "multi.hpp"
 #include "parser.hpp"
 
 using namespace mrt_host;
@@ -17,6 +18,17 @@ static double now() { return std::chrono::duration<double>(std::chrono::steady_c
 
 // CLI::raytrace, cli.rs:155-177: one Sampler, rt.sample passes, optional save per pass, final save
 static double raytrace(const CliArgs& a, const Render& render, const Logger& log) {
+    const std::string out_name = a.output.value_or("out.png");
+    if (a.gpus > 1 && !a.update) {  // one image on several GPUs; --update shows every pass and stays on one GPU
+        std::vector<int> devices;
+        for (int g = 0; g < a.gpus; g++) devices.push_back(a.device + g);
+        MultiSampler multi(devices, (uint32_t)a.worker.value_or(24), (uint32_t)a.dim.value_or(64), a.seed);
+        const double t0 = now();
+        const double dt = multi.execute(render.scene, render.frame, render.rt, render.rt.sample);
+        if (log) log("cli:sample:0.." + std::to_string(render.rt.sample) + " on " + std::to_string(a.gpus) + " gpus: " + std::to_string(dt) + "s");
+        save_image(multi.img(render.frame), out_name);
+        return now() - t0;
+    }
     Sampler sampler((uint32_t)a.worker.value_or(24), (uint32_t)a.dim.value_or(64), a.device, a.seed);
     const std::string out = a.output.value_or("out.png");
     const double t0 = now();
@@ -46,7 +58,7 @@ int main(int argc, char** argv) {
         Logger log;
         if (a.verbose) log = [](const std::string& m) { std::cout << m << std::endl; };
         if (a.http) {  // raytrace.rs:22-30: blocks forever
-            serve(*a.http, a.device, log ? log : Logger([](const std::string& m) { std::cout << m << std::endl; }));
+            serve(*a.http, a.device, a.gpus, log ? log : Logger([](const std::string& m) { std::cout << m << std::endl; }));
             return 0;
         }
         const Json d = merged_description(a);

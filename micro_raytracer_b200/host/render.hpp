@@ -144,10 +144,11 @@ public:
     void set_option(uint32_t option, uint32_t value);
     uint32_t passes();
     mrt_ctx* ctx() { return ctx_; }
+    // upload what changed of the three borrows (what execute does first); for hosts that queue work themselves
+    void bind(const Scene& scene, const Frame& frame, const RayTracer& rt);
 
 private:
     void check(int rc, const char* what);
-    void bind(const Scene& scene, const Frame& frame, const RayTracer& rt);
     mrt_ctx* ctx_ = nullptr;
     uint64_t seed_;
     std::string scene_key_, frame_key_, rt_key_;

@@ -251,3 +251,29 @@ def test_native_http_returns_the_rendered_jpeg(native_server):
     s.execute(r.scene, r.frame, r.rt, 4)
     want = s.img(r.frame).astype(np.float64)
     assert img.shape == want.shape and np.abs(img - want).mean() < 2.0
+
+
+# ----------------------------------------------------------------------------- GPU: several devices, one process
+def _n_devices():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.gpu
+def test_native_multi_gpu_render_equals_the_single_gpu_one(tmp_path):
+    """--gpus N: sample split over N devices + one ncclReduce of the accumulators (host/multi.cpp).
+    The counter-based RNG keys on the global sample index, so only the f32 summation order differs."""
+    from PIL import Image
+    path = os.path.join(SCENES, "CornellBox2.json")
+    args = [path, "--res", "128", "128", "--ssaa", "2", "--sample", "16"]
+    if _n_devices() < 2:
+        p = run(*args, "--gpus", "2", "-o", tmp_path / "x.png", check=False)
+        assert p.returncode == 1 and p.stderr.startswith("cli: ")  # no second device: a clean error, never a fallback
+        pytest.skip("needs two GPUs")
+    run(*args, "-o", tmp_path / "one.png")
+    for g in (2, min(_n_devices(), 8)):
+        p = run(*args, "--gpus", g, "-v", "-o", tmp_path / f"g{g}.png")
+        assert f"on {g} gpus" in p.stdout
+        a = np.asarray(Image.open(tmp_path / "one.png")).astype(int)
+        b = np.asarray(Image.open(tmp_path / f"g{g}.png")).astype(int)
+        assert np.abs(a - b).max() <= 1 and (a == b).mean() > 0.999
