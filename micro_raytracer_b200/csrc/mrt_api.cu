@@ -121,6 +121,7 @@ struct mrt_ctx {
     uint32_t rank = 0, world = 1;
     uint32_t passes = 0;        // passes this context rendered (local)
     uint32_t passes_total = 0;  // passes the accumulator holds (after an external reduce)
+    bool tiled = true;  // warp = 8x4 pixel tile (FilmParams::tiles_x); MRT_TILE=0: 32 pixels of a row (A/B knob)
     uint32_t spp_per_launch = 1024;  // measured: 128 -> 8917, 256 -> 9058, 1024 -> 9234 Mpaths/s (intra-warp tail)
     uint32_t normal_space = MRT_NORMAL_FORWARD_XF;  // MRT_OPT_NORMAL_SPACE
 
@@ -179,6 +180,7 @@ FilmParams make_film_params(const mrt_ctx* c) {
     fp.fh = (float)f.res[1] * f.ssaa;
     const float tan_fov = std::tan((0.5f * f.fov) * (3.14159265358979323846f / 180.0f));  // rt.rs:902
     fp.fy = 1.0f / (2.0f * tan_fov);
+    fp.tiles_x = c->tiled ? (c->nw + 15u) / 16u : 0u;
     return fp;
 }
 
@@ -329,6 +331,7 @@ int mrt_create(mrt_ctx** out, int device, uint32_t workers, uint32_t n_dim) {
         delete c;
         return MRT_ERR_CUDA;
     }
+    if (const char* s = std::getenv("MRT_TILE")) c->tiled = std::atoi(s) != 0;
     if (const char* s = std::getenv("MRT_SPP_PER_LAUNCH")) {
         const int v = std::atoi(s);
         if (v > 0) c->spp_per_launch = (uint32_t)v;

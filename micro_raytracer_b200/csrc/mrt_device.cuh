@@ -146,7 +146,12 @@ struct FilmParams {
     float fw, fh;         // res * ssaa as f32 (rt.rs:938-939)
     float fy;             // 1 / (2 tan(fov/2))  (rt.rs:902-906)
     uint32_t cam_identity;  // cam_M == I: skip the rotation
+    uint32_t tiles_x;       // > 0: a warp renders an 8x4 pixel tile, a block of 128 threads 16x8 (tiles_x blocks per row); 0: 32 pixels of a row
 };
+// number of 128-thread blocks a path-kernel launch needs for this film
+__host__ __device__ inline uint32_t path_grid_blocks(const FilmParams& fp) {
+    return fp.tiles_x ? fp.tiles_x * ((fp.nh + 7u) / 8u) : (fp.nw * fp.nh + 127u) / 128u;
+}
 
 // ------------------------------------------------------------------ small vector helpers
 struct f3 { float x, y, z; };

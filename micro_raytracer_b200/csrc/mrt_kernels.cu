@@ -200,8 +200,8 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
 
 template <uint32_t F>
 cudaError_t launch_path_f(bool in_param, const ParamScene* ps, const GlobalScene* gs, const FilmParams& fp, cudaStream_t st) {
-    const uint32_t npix = fp.nw * fp.nh;
-    const dim3 grid((npix + MRT_PATH_BLOCK - 1) / MRT_PATH_BLOCK), block(MRT_PATH_BLOCK);
+    static_assert(MRT_PATH_BLOCK == 128, "the tiled pixel mapping assumes blocks of four warps");
+    const dim3 grid(path_grid_blocks(fp)), block(MRT_PATH_BLOCK);
     if (in_param) path_kernel_param<F><<<grid, block, 0, st>>>(*ps, fp);
     else path_kernel_global<F><<<grid, block, 0, st>>>(*gs, fp);
     return cudaGetLastError();

@@ -28,10 +28,21 @@ __device__ __forceinline__ void camera_ray(const FilmParams& fp, f3 q, float u1,
 
 template <class V, uint32_t F>
 __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
-    const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t npix = fp.nw * fp.nh;
-    if (pix >= npix || fp.n_samples == 0u) return;
-    const uint32_t py = pix / fp.nw, px = pix - py * fp.nw;
+    // Pixel of this thread.  Tiled: a warp renders an 8x4 tile and a block 16x8, so the lanes of a warp look at
+    // neighbouring surfaces (paths of similar length, similar BVH traversals); the RNG and the accumulator are
+    // keyed by the PIXEL, so the image does not depend on the mapping.
+    uint32_t px, py;
+    if (fp.tiles_x) {
+        const uint32_t by = blockIdx.x / fp.tiles_x, bx = blockIdx.x - by * fp.tiles_x;
+        const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+        px = bx * 16u + (w & 1u) * 8u + (lane & 7u);
+        py = by * 8u + (w >> 1) * 4u + (lane >> 3);
+    } else {
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        py = i / fp.nw; px = i - py * fp.nw;
+    }
+    if (px >= fp.nw || py >= fp.nh || fp.n_samples == 0u) return;
+    const uint32_t pix = py * fp.nw + px;
     const SceneCommon& c = sc.c();
     const f3 q = pixel_focus_vec(fp, px, py);
     const uint32_t cam_seed = cam_hash_seed(pix, fp.key);
