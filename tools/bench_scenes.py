@@ -1,7 +1,7 @@
 """Throughput of every BASELINE.json config (not the headline bench): Mpaths/s per scene on one GPU,
 render-only (CUDA-event seconds returned by mrt_execute), at the configs' full resolutions with a
 bounded number of passes; optionally the oracle's rate on the host cores beside it.
-    python tools/bench_scenes.py [--cpu]
+    python tools/bench_scenes.py [--cpu] [--only Scene] [--passes N]
 """
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -23,10 +23,12 @@ CONFIGS = [
 def main():
     cpu = "--cpu" in sys.argv
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+    force_passes = int(sys.argv[sys.argv.index("--passes") + 1]) if "--passes" in sys.argv else None
     rows = []
     for label, name, res, ssaa, rt, passes in CONFIGS:
         if only and name != only:
             continue
+        passes = force_passes or passes
         r = load(name, res, ssaa, **rt)
         s = mrt.Sampler(device=0)
         s.execute(r.scene, r.frame, r.rt, 1)  # upload + warm-up; starts the background scene specialisation
