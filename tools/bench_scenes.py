@@ -14,10 +14,10 @@ CONFIGS = [
     ("1 Default 1280x720 direct light", "Default", None, None, {}, 256),
     ("2 CornellBox2 1080^2 ssaa2 (headline)", "CornellBox2", None, None, {}, 256),
     ("3 CornellBox (README 10-object) 1920x1080 bounce16", "CornellBox", (1920, 1080), 1.0, {"bounce": 16}, 256),
-    ("4a Mesh 1920x1080", "Mesh", (1920, 1080), 1.0, {}, 32),
-    ("4b Instance (1000 spheres) 1920x1080", "Instance", (1920, 1080), 1.0, {}, 16),
-    ("5a Minecraft 3840x2160 ssaa2", "Minecraft", (3840, 2160), 2.0, {}, 8),
-    ("5b dof 3840x2160", "dof", (3840, 2160), 1.0, {}, 64),
+    ("4a Mesh 1920x1080", "Mesh", (1920, 1080), 1.0, {}, 128),
+    ("4b Instance (1000 spheres) 1920x1080", "Instance", (1920, 1080), 1.0, {}, 128),
+    ("5a Minecraft 3840x2160 ssaa2", "Minecraft", (3840, 2160), 2.0, {}, 64),
+    ("5b dof 3840x2160", "dof", (3840, 2160), 1.0, {}, 128),
 ]
 
 def main():
