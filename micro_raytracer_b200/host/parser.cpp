@@ -33,6 +33,11 @@ static std::string slurp(const std::string& path) {
     return std::string((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
 }
 static float num(const Json& j) { return (float)j.as_num(); }
+static uint32_t u32_of(const Json& j, const char* what) {  // serde: usize / u32 fields reject negatives and fractions
+    const double v = j.as_num();
+    if (!(v >= 0.0 && v <= 4294967295.0) || v != std::floor(v)) throw Error(std::string("invalid value for `") + what + "`: expected an unsigned integer");
+    return (uint32_t)v;
+}
 
 template <size_t N>
 static std::array<float, N> vec(const Json& j, const char* what) {
@@ -105,8 +110,8 @@ static Json inline_json(const std::string& s) { return Json::parse(gunzip(base64
 static TexturePtr texture(const Json& v, const std::string& base_dir) {
     if (v.is_obj()) {
         auto t = std::make_shared<Texture>();
-        if (const Json* w = v.find("w")) t->w = (uint32_t)w->as_num();
-        if (const Json* h = v.find("h")) t->h = (uint32_t)h->as_num();
+        if (const Json* w = v.find("w")) t->w = u32_of(*w, "w");
+        if (const Json* h = v.find("h")) t->h = u32_of(*h, "h");
         if (const Json* d = v.find("dat")) { t->has_dat = true; flatten(*d, t->dat); }
         return t;
     }
@@ -257,8 +262,8 @@ Render render_from_json(const Json& d, const std::string& base_dir) {
     Render out;
     if (!d.is_obj()) throw Error("invalid type: expected a render description object");
     if (const Json* rt = d.find("rt")) {
-        if (const Json* v = rt->find("bounce")) out.rt.bounce = (uint32_t)v->as_num();
-        if (const Json* v = rt->find("sample")) out.rt.sample = (uint32_t)v->as_num();
+        if (const Json* v = rt->find("bounce")) out.rt.bounce = u32_of(*v, "bounce");
+        if (const Json* v = rt->find("sample")) out.rt.sample = u32_of(*v, "sample");
         if (const Json* v = rt->find("loss")) out.rt.loss = num(*v);
     }
     if (const Json* fr = d.find("frame")) {
