@@ -241,6 +241,7 @@ bool all_finite(const float* v, int n) {
 // ---- BVH builder (scene-level BVH over the finite instances, triangle BVHs of the meshes; mrt_device.cuh:
 // BvhNode): median split of the centroids along the widest axis, one primitive per leaf (measured best).
 struct PrimBox { float lo[3], hi[3]; uint32_t ref; };
+bool g_bvh_sah = true;  // MRT_BVH_SAH=0: median splits only (A/B knob, read in mrt_create)
 // Returns the reference of the subtree over prims[begin, end): a leaf (MRT_BVH_LEAF | prims[begin].ref) for a
 // single primitive, else the index of a node that holds the boxes and references of its two halves.
 uint32_t bvh_build(std::vector<PrimBox>& prims, size_t begin, size_t end, std::vector<BvhNode>* nodes, int depth = 0, int* max_depth = nullptr) {
@@ -255,10 +256,65 @@ uint32_t bvh_build(std::vector<PrimBox>& prims, size_t begin, size_t end, std::v
     int ax = 0;
     if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
     if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
-    const size_t mid = begin + (end - begin) / 2;
-    std::nth_element(prims.begin() + begin, prims.begin() + mid, prims.begin() + end, [ax](const PrimBox& a, const PrimBox& b) {
-        return a.lo[ax] + a.hi[ax] < b.lo[ax] + b.hi[ax];
-    });
+    size_t mid = begin + (end - begin) / 2;
+    bool split_done = false;
+    if (g_bvh_sah && end - begin > 4) {
+        // binned surface-area heuristic over the three axes (16 bins of the centroid range); falls back to the
+        // median when every centroid lands in one bin or the best split is lopsided beyond the stack's depth budget
+        constexpr int NB = 16;
+        float best_cost = INFINITY; int best_ax = -1, best_bin = -1;
+        for (int a = 0; a < 3; a++) {
+            const float ext = chi[a] - clo[a];
+            if (!(ext > 0.0f)) continue;
+            struct Bin { float lo[3], hi[3]; size_t n; } bins[NB];
+            for (auto& b : bins) { for (int k = 0; k < 3; k++) { b.lo[k] = INFINITY; b.hi[k] = -INFINITY; } b.n = 0; }
+            const float scale = (float)NB / ext;
+            for (size_t i = begin; i < end; i++) {
+                const float cc = 0.5f * (prims[i].lo[a] + prims[i].hi[a]);
+                const int bi = std::min(NB - 1, std::max(0, (int)((cc - clo[a]) * scale)));
+                Bin& b = bins[bi];
+                for (int k = 0; k < 3; k++) { b.lo[k] = std::fmin(b.lo[k], prims[i].lo[k]); b.hi[k] = std::fmax(b.hi[k], prims[i].hi[k]); }
+                b.n++;
+            }
+            auto area = [](const float* lo, const float* hi) {
+                const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+                return dx * dy + dy * dz + dz * dx;
+            };
+            float la[NB], ra[NB]; size_t ln[NB], rn[NB];
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}; size_t n = 0;
+            for (int b = 0; b < NB; b++) {
+                if (bins[b].n) for (int k = 0; k < 3; k++) { lo[k] = std::fmin(lo[k], bins[b].lo[k]); hi[k] = std::fmax(hi[k], bins[b].hi[k]); }
+                n += bins[b].n; ln[b] = n; la[b] = n ? area(lo, hi) : 0.0f;
+            }
+            for (int k = 0; k < 3; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; } n = 0;
+            for (int b = NB - 1; b >= 0; b--) {
+                if (bins[b].n) for (int k = 0; k < 3; k++) { lo[k] = std::fmin(lo[k], bins[b].lo[k]); hi[k] = std::fmax(hi[k], bins[b].hi[k]); }
+                n += bins[b].n; rn[b] = n; ra[b] = n ? area(lo, hi) : 0.0f;
+            }
+            for (int b = 0; b + 1 < NB; b++) {  // split after bin b
+                if (ln[b] == 0 || rn[b + 1] == 0) continue;
+                const float cost = la[b] * (float)ln[b] + ra[b + 1] * (float)rn[b + 1];
+                if (cost < best_cost) { best_cost = cost; best_ax = a; best_bin = b; }
+            }
+        }
+        if (best_ax >= 0) {
+            const int a = best_ax;
+            const float scale = 16.0f / (chi[a] - clo[a]), c0 = clo[a];
+            auto it = std::partition(prims.begin() + begin, prims.begin() + end, [&](const PrimBox& p) {
+                const float cc = 0.5f * (p.lo[a] + p.hi[a]);
+                return std::min(15, std::max(0, (int)((cc - c0) * scale))) <= best_bin;
+            });
+            const size_t m = (size_t)(it - prims.begin());
+            const size_t small = std::min(m - begin, end - m);
+            if (m > begin && m < end && small * 16 >= (end - begin) / 4 + 1) { mid = m; split_done = true; }  // keep the depth bounded
+        }
+    }
+    if (!split_done) {
+        mid = begin + (end - begin) / 2;
+        std::nth_element(prims.begin() + begin, prims.begin() + mid, prims.begin() + end, [ax](const PrimBox& a, const PrimBox& b) {
+            return a.lo[ax] + a.hi[ax] < b.lo[ax] + b.hi[ax];
+        });
+    }
     auto bounds = [&](size_t b0, size_t e0, float* lo, float* hi) {
         for (int a = 0; a < 3; a++) { lo[a] = INFINITY; hi[a] = -INFINITY; }
         for (size_t i = b0; i < e0; i++)
@@ -332,6 +388,7 @@ int mrt_create(mrt_ctx** out, int device, uint32_t workers, uint32_t n_dim) {
         return MRT_ERR_CUDA;
     }
     if (const char* s = std::getenv("MRT_TILE")) c->tiled = std::atoi(s) != 0;
+    if (const char* s = std::getenv("MRT_BVH_SAH")) g_bvh_sah = std::atoi(s) != 0;
     if (const char* s = std::getenv("MRT_SPP_PER_LAUNCH")) {
         const int v = std::atoi(s);
         if (v > 0) c->spp_per_launch = (uint32_t)v;
