@@ -160,7 +160,7 @@ int mrt_set_rt(mrt_ctx* ctx, uint32_t bounce, float loss, uint64_t seed);
  *     MRT_NORMAL_FORWARD_XF  norm(rot_y * (look * n)) — rt.rs:792 as written at HEAD (default)
  *     MRT_NORMAL_OBJECT      norm(n) — what the revision that rendered doc/out3.png (README's
  *                            CornellBox2 image) did; kept so that golden image stays reproducible.
- *   MRT_OPT_JIT            scene-specialised path kernel: for scenes of <= 128 primitives the library can
+ *   MRT_OPT_JIT            scene-specialised path kernel: for small scenes (those not searched through the BVH) the library can
  *                          compile the instance tables INTO the kernel at run time (NVRTC, ~0.15 s; cached per
  *                          scene in the process and as a cubin under $MRT_JIT_CACHE | ~/.cache/mrt_b200).
  *                          Same arithmetic, same results to rounding; only the instruction stream differs

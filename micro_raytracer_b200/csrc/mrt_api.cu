@@ -659,9 +659,14 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     // scene-level BVH: only for scenes too large to unroll (the specialised kernel covers <= 128 primitives)
     std::vector<BvhNode> bvh_nodes;
     uint32_t bvh_root = 0;
-    size_t bvh_min = 128;  // the specialised (unrolled) kernel covers up to 128 primitives
+    // BVH or brute force?  Measured on random scenes of N boxes / N spheres (unrolled specialised kernel vs BVH with
+    // the generic kernel, Mpaths/s): boxes 48: 11 391 / 8 191, 64: 6 801 / 6 418, 96: 3 477 / 4 929; spheres 32: 14 105 /
+    // 13 402, 48: 8 483 / 9 141, 64: 5 608 / 7 393 — the cross-over sits at ~72 box-equivalents (a sphere test costs 1.5
+    // slab tests, a rotated box 2, a mesh far more).  Minecraft.json (84 boxes): 4 144 unrolled, 4 556 through the BVH.
+    size_t bvh_min = 72;
     if (const char* e = std::getenv("MRT_BVH_MIN")) bvh_min = (size_t)std::max(0, std::atoi(e));  // experiment knob
-    bool use_bvh = prim_boxes.size() > bvh_min && prim_boxes_ok && prim_boxes.size() < (1u << 28) && !std::getenv("MRT_NO_BVH");
+    const size_t brute_cost = by_kind[K_BOX].size() + (3 * by_kind[K_SPHERE].size()) / 2 + 2 * bxf.size() + 4 * by_kind[K_MESH].size();
+    bool use_bvh = brute_cost > bvh_min && prim_boxes.size() > 1 && prim_boxes_ok && prim_boxes.size() < (1u << 28) && !std::getenv("MRT_NO_BVH");
     if (use_bvh) {
         int depth = 0;
         bvh_root = bvh_build(prim_boxes, 0, prim_boxes.size(), &bvh_nodes, 0, &depth);
@@ -688,7 +693,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     c->jit_err.clear();
     {
         const size_t n_prim = 2 * boxp.size() + by_kind[K_SPHERE].size() + by_kind[K_PLANE].size() + bxf.size() + by_kind[K_MESH].size();
-        bool ok = n_prim > 0 && n_prim <= 128;
+        bool ok = n_prim > 0 && n_prim <= 128 && !use_bvh;  // scenes that go through the BVH use the generic kernel
         std::string h = "// generated by mrt_set_scene\n";
         auto tab = [&](const char* name, size_t n, auto&& row) {
             h += std::string("#define ") + name + "(X)";

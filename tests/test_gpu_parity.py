@@ -474,6 +474,7 @@ def test_cluster_culling_in_the_specialised_kernel_changes_nothing(seed, monkeyp
                               "scene": {"renderer": objs, "light": [{"type": "dir", "dir": [0.3, 0.5, -1]}],
                                         "sky": {"color": [0.3, 0.4, 0.6], "pwr": 0.5}}})
     monkeypatch.setenv("MRT_JIT_CACHE", str(tmp_path))
+    monkeypatch.setenv("MRT_BVH_MIN", "1000")  # keep the larger scenes on the unrolled kernel (by default > 72 boxes go through the BVH)
     res = {}
     for cl in ("4", "0"):
         monkeypatch.setenv("MRT_JIT_CLUSTER", cl)

@@ -277,3 +277,42 @@ def test_native_multi_gpu_render_equals_the_single_gpu_one(tmp_path):
         a = np.asarray(Image.open(tmp_path / "one.png")).astype(int)
         b = np.asarray(Image.open(tmp_path / f"g{g}.png")).astype(int)
         assert np.abs(a - b).max() <= 1 and (a == b).mean() > 0.999
+
+
+# ----------------------------------------------------------------------------- the host as a library
+def _build_api_example(tmp_path):
+    exe = tmp_path / "api_example"
+    pkg = os.path.join(ROOT, "micro_raytracer_b200")
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O1", "-pthread", os.path.join(ROOT, "tests", "native", "api_example.cpp"),
+           "-I", os.path.join(pkg, "host"), "-L", pkg, "-lmrt_host", "-lmrt", "-lz", "-ldl", f"-Wl,-rpath,{pkg}", "-o", str(exe)]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    return exe
+
+
+def test_host_library_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """libmrt_host.a + the headers of micro_raytracer_b200/host are a usable C++ API (mrt_host::Sampler ≙ src/sampler.rs).
+    Without a device the program reports the error and exits 1 — there is no CPU path to fall back to."""
+    exe = _build_api_example(tmp_path)
+    from util import have_gpu
+    if have_gpu():
+        pytest.skip("GPU present: covered by test_host_library_api")
+    p = subprocess.run([exe, os.path.join(SCENES, "Default.json"), "2", tmp_path / "o.ppm"], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 1 and "no CUDA device" in p.stderr and not (tmp_path / "o.ppm").exists()
+
+
+@pytest.mark.gpu
+def test_host_library_api(tmp_path):
+    """Pass-by-pass execute + img through mrt_host::Sampler give the image the Python mirror gives."""
+    from PIL import Image
+    exe = _build_api_example(tmp_path)
+    out = tmp_path / "o.ppm"
+    p = subprocess.run([exe, os.path.join(SCENES, "dof.json"), "3", out], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert "passes 3" in p.stdout
+    r = mrt.load_render(os.path.join(SCENES, "dof.json"))
+    r.frame.res = (96, 54)
+    s = mrt.Sampler(device=0)
+    for _ in range(3):
+        s.execute(r.scene, r.frame, r.rt)
+    assert np.array_equal(np.asarray(Image.open(out).convert("RGB")), s.img(r.frame))
