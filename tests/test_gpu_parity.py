@@ -86,7 +86,7 @@ def test_shared_rng_paths_match_oracle(pair, name, res, ssaa):
     assert np.isfinite(ag).all()
     st = gpu.jit_status()
     assert st["compiled"] == (gpu.jit_expected and st["eligible"]), st
-    if name != "Instance":
+    if name not in ("Instance", "Minecraft"):  # these two go through the scene BVH (generic kernel)
         assert st["eligible"]
     ok = np.abs(ag - ac).max(axis=2) <= 1e-3 + 2e-3 * np.abs(ac).max(axis=2)
     assert ok.mean() >= 0.95, f"{name}: only {ok.mean():.4%} pixels match"
