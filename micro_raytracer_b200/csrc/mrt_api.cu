@@ -693,8 +693,13 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     c->jit_err.clear();
     {
         const size_t n_prim = 2 * boxp.size() + by_kind[K_SPHERE].size() + by_kind[K_PLANE].size() + bxf.size() + by_kind[K_MESH].size();
-        bool ok = n_prim > 0 && n_prim <= 128 && !use_bvh;  // scenes that go through the BVH use the generic kernel
+        // Scenes that go through the BVH get a specialised kernel too, but one that only folds what does not
+        // depend on the instance tables (kinds present, material scalars, lights, sky, rotation class): their
+        // header has empty tables, so scenes of the same shape share one kernel.
+        bool ok = n_prim > 0 && (n_prim <= 128 || use_bvh);
         std::string h = "// generated by mrt_set_scene\n";
+        if (use_bvh) h += "#define MRT_JIT_BVH 1\n";
+        const bool tables = !use_bvh;
         auto tab = [&](const char* name, size_t n, auto&& row) {
             h += std::string("#define ") + name + "(X)";
             for (size_t k = 0; k < n; k++) { h += " X(" + std::to_string(k); row(k); h += ")"; }
@@ -709,7 +714,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
         size_t cluster = 4;
         if (const char* e = std::getenv("MRT_JIT_CLUSTER")) cluster = (size_t)std::max(0, std::atoi(e));  // experiment knob, 0 = off
         const bool clustered = cluster > 0 && boxp.size() >= 3 * cluster;
-        for (size_t k = 0; k < boxp.size(); k++) {
+        for (size_t k = 0; tables && k < boxp.size(); k++) {
             const float* q = &boxp[k].q0.x;  // (cA.x,cB.x, cA.y,cB.y, cA.z,cB.z, hA.x,hB.x, hA.y,hB.y, hA.z,hB.z)
             ok &= all_finite(q, 12);
             const bool odd = 2 * k + 1 >= by_kind[K_BOX].size();
@@ -748,16 +753,16 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
             if (clustered && (k % cluster == cluster - 1 || k + 1 == boxp.size())) h += " CE";
         }
         h += "\n";
-        tab("MRT_JIT_SPHERES", by_kind[K_SPHERE].size(), [&](size_t k) {
+        tab("MRT_JIT_SPHERES", tables ? by_kind[K_SPHERE].size() : 0, [&](size_t k) {
             const SlimInst& e = by_kind[K_SPHERE][k];
             const float v[4] = {e.a.x, e.a.y, e.a.z, e.b.x};
             ok &= all_finite(v, 4); lits(&h, v, 4); });
-        tab("MRT_JIT_PLANES", by_kind[K_PLANE].size(), [&](size_t k) {
+        tab("MRT_JIT_PLANES", tables ? by_kind[K_PLANE].size() : 0, [&](size_t k) {
             const SlimInst& e = by_kind[K_PLANE][k];
             const float v[4] = {e.a.x, e.a.y, e.a.z, e.b.x};
             ok &= all_finite(v, 4); lits(&h, v, 4); });
-        tab("MRT_JIT_BXFS", bxf.size(), [&](size_t k) { ok &= all_finite(&bxf[k].r0.x, 15); lits(&h, &bxf[k].r0.x, 12); lits(&h, &bxf[k].h.x, 3); });
-        tab("MRT_JIT_MESHES", by_kind[K_MESH].size(), [&](size_t k) {
+        tab("MRT_JIT_BXFS", tables ? bxf.size() : 0, [&](size_t k) { ok &= all_finite(&bxf[k].r0.x, 15); lits(&h, &bxf[k].r0.x, 12); lits(&h, &bxf[k].h.x, 3); });
+        tab("MRT_JIT_MESHES", tables ? by_kind[K_MESH].size() : 0, [&](size_t k) {
             const SlimInst& e = by_kind[K_MESH][k];
             ok &= all_finite(&e.a.x, 3) && all_finite(mesh_m[k].m, 12);
             lits(&h, &e.a.x, 3);
@@ -767,7 +772,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
             lits(&h, mesh_m[k].m, 12); });
         // big unrolled scenes: without a register budget ptxas hoists every operand (254 registers, 2 blocks
         // per SM on Minecraft.json); 3 blocks (168 registers) measured best there: 2594 -> 2757 Mpaths/s
-        if (n_prim > 48 && !(std::getenv("MRT_JIT_MINBLOCKS") && *std::getenv("MRT_JIT_MINBLOCKS"))) h += "#define MRT_JIT_MINBLOCKS 3\n";
+        if (tables && n_prim > 48 && !(std::getenv("MRT_JIT_MINBLOCKS") && *std::getenv("MRT_JIT_MINBLOCKS"))) h += "#define MRT_JIT_MINBLOCKS 3\n";
         {   // rough/metal/glass/opacity shared by every material (and no map overrides them): fold them in
             bool uni = s->n_objects > 0;
             const mrt_material& m0 = s->objects[0].mat;
@@ -796,6 +801,12 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
         h += "#define MRT_JIT_ROT " + std::to_string(rot_class) + "\n";
         h += "#define MRT_JIT_N_BOX " + std::to_string(cnt[K_BOX] + cnt[K_BOX_XF]) + "\n";
         h += "#define MRT_JIT_N_SPHERE " + std::to_string(cnt[K_SPHERE]) + "\n";
+        if (use_bvh) {  // what the BVH leaves and the loops around the traversal may assume
+            h += "#define MRT_JIT_N_ABOX " + std::to_string(cnt[K_BOX]) + "\n";
+            h += "#define MRT_JIT_N_BXF " + std::to_string(cnt[K_BOX_XF]) + "\n";
+            h += "#define MRT_JIT_N_MESH " + std::to_string(cnt[K_MESH]) + "\n";
+            h += "#define MRT_JIT_N_LIGHTS " + std::to_string(s->n_lights) + "\n";
+        }
         h += "#define MRT_JIT_N_PLANE " + std::to_string(cnt[K_PLANE]) + "\n";
         h += "#define MRT_JIT_FIRST_SPHERE " + std::to_string(first[K_SPHERE]) + "\n";
         h += "#define MRT_JIT_FIRST_PLANE " + std::to_string(first[K_PLANE]) + "\n";
@@ -919,7 +930,8 @@ int mrt_execute_async(mrt_ctx* c, uint32_t n_passes) {
         fp.sample0 = c->rank + c->passes * c->world;
         fp.sample_stride = c->world;
         fp.n_samples = n;
-        cudaError_t e = use_jit ? mrt_jit_launch(c->jit_kernel, c->gscene.c, fp, c->stream)
+        cudaError_t e = use_jit ? (c->gscene.bvh ? mrt_jit_launch_bvh(c->jit_kernel, c->gscene, fp, c->stream)
+                                                 : mrt_jit_launch(c->jit_kernel, c->gscene.c, fp, c->stream))
                                 : mrt_launch_path(c->features, c->in_param, c->pscene, &c->gscene, fp, c->stream);
         if (e != cudaSuccess) return cuda_fail(c, e, "path kernel launch");
         if (use_jit) c->jit_launches++;

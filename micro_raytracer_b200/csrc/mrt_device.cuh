@@ -684,6 +684,25 @@ __device__ __forceinline__ bool bracket_hit(const RayPre& r, float4 lo, float4 h
     const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
     return tn <= tf && tf >= 0.0f && tn <= best;
 }
+// What the specialised kernel of a BVH scene knows about the scene's shape (mrt_api.cu: MRT_JIT_BVH header):
+// kinds that do not occur cost nothing in the leaves, plane and light loops have literal trip counts.
+#if defined(MRT_JIT) && defined(MRT_JIT_BVH)
+#define MRT_BVH_HAS_ABOX (MRT_JIT_N_ABOX > 0)
+#define MRT_BVH_HAS_SPHERE (MRT_JIT_N_SPHERE > 0)
+#define MRT_BVH_HAS_BXF (MRT_JIT_N_BXF > 0)
+#define MRT_BVH_HAS_MESH (MRT_JIT_N_MESH > 0)
+#define MRT_N_PLANES(c) ((uint32_t)MRT_JIT_N_PLANE)
+#define MRT_N_LIGHTS(c) ((uint32_t)MRT_JIT_N_LIGHTS)
+#define MRT_BVH_ALWAYS true   // no brute-force path in this kernel
+#else
+#define MRT_BVH_HAS_ABOX true
+#define MRT_BVH_HAS_SPHERE true
+#define MRT_BVH_HAS_BXF true
+#define MRT_BVH_HAS_MESH true
+#define MRT_N_PLANES(c) ((c).cnt[K_PLANE])
+#define MRT_N_LIGHTS(c) ((c).n_lights)
+#define MRT_BVH_ALWAYS false
+#endif
 template <uint32_t F, bool ANY, bool WANT_T1>
 __device__ __forceinline__ void bvh_leaf(Best& B, const GlobalScene& s, const RayPre& r, const RayPk& rp, uint32_t ref) {
     const SceneCommon& c = s.c;
@@ -691,7 +710,9 @@ __device__ __forceinline__ void bvh_leaf(Best& B, const GlobalScene& s, const Ra
     float t0 = 0.f, t1 = 0.f;
     int tr0 = -1, tr1 = -1;
     bool hit;
-    if (kind == K_BOX) {  // one lane of a BoxPair, scalar form of test_box_pair
+    constexpr bool only_abox = MRT_BVH_HAS_ABOX && !MRT_BVH_HAS_SPHERE && !MRT_BVH_HAS_BXF && !MRT_BVH_HAS_MESH;
+    constexpr bool only_sphere = MRT_BVH_HAS_SPHERE && !MRT_BVH_HAS_ABOX && !MRT_BVH_HAS_BXF && !MRT_BVH_HAS_MESH;
+    if (MRT_BVH_HAS_ABOX && (only_abox || kind == K_BOX)) {  // one lane of a BoxPair, scalar form of test_box_pair
         const float* q = reinterpret_cast<const float*>(s.boxp + (k >> 1)) + (k & 1u);
         const float cx = fmaf(__ldg(q + 0), r.m.x, r.nom.x), cy = fmaf(__ldg(q + 2), r.m.y, r.nom.y), cz = fmaf(__ldg(q + 4), r.m.z, r.nom.z);
         const float hx = __ldg(q + 6), hy = __ldg(q + 8), hz = __ldg(q + 10);
@@ -699,7 +720,7 @@ __device__ __forceinline__ void bvh_leaf(Best& B, const GlobalScene& s, const Ra
         t1 = fminf(fminf(fmaf(hx, r.am.x, cx), fmaf(hy, r.am.y, cy)), fmaf(hz, r.am.z, cz));
         hit = fmaxf(t0, 0.0f) <= t1 && t0 < t1;  // as best_update_slab: t0 == t1 (edge graze) is a miss
         best_update_lex<F, ANY, WANT_T1>(B, hit, t0, t1, (int)k, -1, -1);
-    } else if (kind == K_SPHERE) {
+    } else if (MRT_BVH_HAS_SPHERE && (only_sphere || kind == K_SPHERE)) {
         const SlimInst e = ldg_slim(s.sph + k);
         const f3 oc = r.o - xyz(e.a);
         const float hb = dot(oc, r.d);
@@ -708,11 +729,11 @@ __device__ __forceinline__ void bvh_leaf(Best& B, const GlobalScene& s, const Ra
         const float sq = sqrtf(fmaxf(disc, 0.0f));
         t0 = -hb - sq;
         best_update_lex<F, ANY, WANT_T1>(B, (disc >= 0.0f) && (t0 >= 0.0f), t0, sq - hb, (int)(c.first[K_SPHERE] + k), -1, -1);
-    } else if (kind == K_BOX_XF) {
+    } else if (MRT_BVH_HAS_BXF && kind == K_BOX_XF) {
         Best L; L.t0 = __int_as_float(0x7f800000); L.t1 = 0.f; L.bi = -1; L.tr0 = L.tr1 = -1; L.any = false;
         test_bxf<F, false, true, false>(L, rp, {__ldg(&s.bxf[k].r0), __ldg(&s.bxf[k].r1), __ldg(&s.bxf[k].r2), __ldg(&s.bxf[k].h)}, 0);
         best_update_lex<F, ANY, WANT_T1>(B, L.bi == 0, L.t0, L.t1, (int)(c.first[K_BOX_XF] + k), -1, -1);
-    } else {
+    } else if (MRT_BVH_HAS_MESH) {
         if constexpr ((F & F_MESH) != 0) {
             const SlimInst e = ldg_slim(s.mesh + k);
             f3 ol = r.o - xyz(e.a), dl = r.d;
@@ -844,9 +865,9 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
 #define E_BXF(k, LE) test_bxf<F, ANY, WANT_T1, LE>(B, rp, sc.bxf(k), (int)(c.first[K_BOX_XF] + (k)));
 #define E_MSH(k, LE) test_mesh<F, ANY, WANT_T1, LE>(B, c, r, sc.mesh(k), sc.mesh_m(k), (int)(c.first[K_MESH] + (k)));
     if constexpr (V::kBvh) {
-        if (sc.s.bvh != nullptr) {  // warp-uniform: large scenes only
+        if (MRT_BVH_ALWAYS || sc.s.bvh != nullptr) {  // warp-uniform: large scenes only
             bvh_traverse<F, ANY, WANT_T1>(B, sc.s, r, rp);
-            for (uint32_t k = 0; k < c.cnt[K_PLANE]; k++) {  // planes are infinite: brute force, same tie rule
+            for (uint32_t k = 0; k < MRT_N_PLANES(c); k++) {  // planes are infinite: brute force, same tie rule
                 const SlimInst e = sc.pln(k);
                 const float t0 = (e.b.x - dot(r.o, xyz(e.a))) * frcp(dot(r.d, xyz(e.a)));
                 best_update_lex<F, ANY, WANT_T1>(B, t0 > 0.0f, t0, t0, (int)(c.first[K_PLANE] + k), -1, -1);
@@ -856,7 +877,7 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
             return B.bi >= 0;
         }
     }
-    if constexpr (!V::kJit) {
+    if constexpr (!V::kJit && !(V::kBvh && MRT_BVH_ALWAYS)) {
         MRT_DUFF((c.cnt[K_BOX] + 1u) >> 1, E_BOX)
         MRT_DUFF(c.cnt[K_SPHERE], E_SPH)
         MRT_DUFF(c.cnt[K_PLANE], E_PLN)

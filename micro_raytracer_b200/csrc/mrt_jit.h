@@ -16,3 +16,5 @@ cudaKernel_t mrt_jit_kernel(const std::string& scene_header, bool wait, MrtJitIn
 // Blocks until a compile started for `scene_header` (if any) is over.
 void mrt_jit_wait(const std::string& scene_header);
 cudaError_t mrt_jit_launch(cudaKernel_t k, const SceneCommon& scene, const FilmParams& fp, cudaStream_t st);
+// the kernel of a BVH scene (header with MRT_JIT_BVH) takes the whole GlobalScene
+cudaError_t mrt_jit_launch_bvh(cudaKernel_t k, const GlobalScene& scene, const FilmParams& fp, cudaStream_t st);

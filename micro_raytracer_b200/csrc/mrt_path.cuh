@@ -96,7 +96,7 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
             // light visibility from the entry hit, rt.rs:1027-1045 (no distance limit)
             uint32_t vis = 0;
             if constexpr ((F & F_LIGHTS) != 0) {
-                for (uint32_t li = 0; li < c.n_lights; li++) {
+                for (uint32_t li = 0; li < MRT_N_LIGHTS(c); li++) {
                     const float4 lv = c.light[li].v_kind;
                     f3 l = (__float_as_uint(lv.w) == 0u) ? normalize(xyz(lv) - hp) : xyz(lv);
                     HitRec dummy;
@@ -158,7 +158,7 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
             {
                 if constexpr ((F & F_LIGHTS) != 0) {
                     f3 lc = mk(0.f, 0.f, 0.f);
-                    for (uint32_t li = 0; li < c.n_lights; li++) {
+                    for (uint32_t li = 0; li < MRT_N_LIGHTS(c); li++) {
                         if (!((vis >> li) & 1u)) continue;
                         const float4 lv = c.light[li].v_kind;
                         const float4 cp = c.light[li].color_pwr;
