@@ -659,13 +659,14 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     // scene-level BVH: only for scenes too large to unroll (the specialised kernel covers <= 128 primitives)
     std::vector<BvhNode> bvh_nodes;
     uint32_t bvh_root = 0;
-    // BVH or brute force?  Measured on random scenes of N boxes / N spheres (unrolled specialised kernel vs BVH with
-    // the generic kernel, Mpaths/s): boxes 48: 11 391 / 8 191, 64: 6 801 / 6 418, 96: 3 477 / 4 929; spheres 32: 14 105 /
-    // 13 402, 48: 8 483 / 9 141, 64: 5 608 / 7 393 — the cross-over sits at ~72 box-equivalents (a sphere test costs 1.5
-    // slab tests, a rotated box 2, a mesh far more).  Minecraft.json (84 boxes): 4 144 unrolled, 4 556 through the BVH.
-    size_t bvh_min = 72;
+    // BVH or brute force?  Measured on random scenes of N boxes / N spheres, both through their specialised kernels
+    // (unrolled / BVH, Mpaths/s): boxes 48: 11 584 / 9 157, 56: 8 621 / 8 264, 64: 6 695 / 7 307; spheres 16: 26 240 /
+    // 24 744, 24: 17 986 / 18 105, 32: 14 179 / 14 699, 40: 10 865 / 12 521, 64: 5 658 / 8 041 — the cross-over sits at
+    // ~60 boxes or ~26 spheres, i.e. ~60 box-equivalents with a sphere at 2.3 (a rotated box 2.5, a mesh far more).
+    // Minecraft.json (84 boxes): 4 144 unrolled, 5 343 through the BVH.
+    size_t bvh_min = 60;
     if (const char* e = std::getenv("MRT_BVH_MIN")) bvh_min = (size_t)std::max(0, std::atoi(e));  // experiment knob
-    const size_t brute_cost = by_kind[K_BOX].size() + (3 * by_kind[K_SPHERE].size()) / 2 + 2 * bxf.size() + 4 * by_kind[K_MESH].size();
+    const size_t brute_cost = (6 * by_kind[K_BOX].size() + 14 * by_kind[K_SPHERE].size() + 15 * bxf.size() + 36 * by_kind[K_MESH].size()) / 6;
     bool use_bvh = brute_cost > bvh_min && prim_boxes.size() > 1 && prim_boxes_ok && prim_boxes.size() < (1u << 28) && !std::getenv("MRT_NO_BVH");
     if (use_bvh) {
         int depth = 0;
