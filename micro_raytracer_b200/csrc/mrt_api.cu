@@ -833,7 +833,7 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
         sc.light[i].color_pwr = make_float4(l.color[0], l.color[1], l.color[2], l.pwr);
     }
     c->gscene.c = sc;
-    c->gscene.boxp = c->d_boxp.p; c->gscene.sph = c->d_slim[K_SPHERE].p; c->gscene.pln = c->d_slim[K_PLANE].p;
+    c->gscene.boxp = c->d_boxp.p; c->gscene.box = c->d_slim[K_BOX].p; c->gscene.sph = c->d_slim[K_SPHERE].p; c->gscene.pln = c->d_slim[K_PLANE].p;
     c->gscene.bxf = c->d_bxf.p;
     c->gscene.bvh = use_bvh ? c->d_bvh.p : nullptr;
     c->gscene.bvh_root = bvh_root;

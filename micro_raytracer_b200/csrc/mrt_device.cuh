@@ -124,6 +124,7 @@ static_assert(sizeof(ParamScene) + 256 < 32764, "kernel parameters are limited t
 struct GlobalScene {
     SceneCommon c;
     const BoxPair* boxp;
+    const SlimInst* box;       // the same axis-aligned boxes one by one (a = centre.xyz, half.x; b.xy = half.yz): what a BVH leaf reads
     const SlimInst* sph;
     const SlimInst* pln;
     const BxfInst* bxf;
@@ -713,9 +714,9 @@ __device__ __forceinline__ void bvh_leaf(Best& B, const GlobalScene& s, const Ra
     constexpr bool only_abox = MRT_BVH_HAS_ABOX && !MRT_BVH_HAS_SPHERE && !MRT_BVH_HAS_BXF && !MRT_BVH_HAS_MESH;
     constexpr bool only_sphere = MRT_BVH_HAS_SPHERE && !MRT_BVH_HAS_ABOX && !MRT_BVH_HAS_BXF && !MRT_BVH_HAS_MESH;
     if (MRT_BVH_HAS_ABOX && (only_abox || kind == K_BOX)) {  // one lane of a BoxPair, scalar form of test_box_pair
-        const float* q = reinterpret_cast<const float*>(s.boxp + (k >> 1)) + (k & 1u);
-        const float cx = fmaf(__ldg(q + 0), r.m.x, r.nom.x), cy = fmaf(__ldg(q + 2), r.m.y, r.nom.y), cz = fmaf(__ldg(q + 4), r.m.z, r.nom.z);
-        const float hx = __ldg(q + 6), hy = __ldg(q + 8), hz = __ldg(q + 10);
+        const SlimInst e = ldg_slim(s.box + k);  // two 16-byte loads; same arithmetic as one lane of test_box_pair
+        const float cx = fmaf(e.a.x, r.m.x, r.nom.x), cy = fmaf(e.a.y, r.m.y, r.nom.y), cz = fmaf(e.a.z, r.m.z, r.nom.z);
+        const float hx = e.a.w, hy = e.b.x, hz = e.b.y;
         t0 = fmaxf(fmaxf(fmaf(hx, r.nam.x, cx), fmaf(hy, r.nam.y, cy)), fmaf(hz, r.nam.z, cz));
         t1 = fminf(fminf(fmaf(hx, r.am.x, cx), fmaf(hy, r.am.y, cy)), fmaf(hz, r.am.z, cz));
         hit = fmaxf(t0, 0.0f) <= t1 && t0 < t1;  // as best_update_slab: t0 == t1 (edge graze) is a miss
