@@ -773,6 +773,9 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
             lits(&h, mesh_m[k].m, 12); });
         // big unrolled scenes: without a register budget ptxas hoists every operand (254 registers, 2 blocks
         // per SM on Minecraft.json); 3 blocks (168 registers) measured best there: 2594 -> 2757 Mpaths/s
+        // BVH kernels are latency bound (long_scoreboard): 64 registers / 8 blocks per SM measured best
+        // (Minecraft.json 5 429 -> 5 628, Instance.json 2 378 -> 2 401 Mpaths/s against ptxas' own 96 / 64)
+        if (use_bvh && !(std::getenv("MRT_JIT_MINBLOCKS") && *std::getenv("MRT_JIT_MINBLOCKS"))) h += "#define MRT_JIT_MINBLOCKS 8\n";
         if (tables && n_prim > 48 && !(std::getenv("MRT_JIT_MINBLOCKS") && *std::getenv("MRT_JIT_MINBLOCKS"))) h += "#define MRT_JIT_MINBLOCKS 3\n";
         {   // rough/metal/glass/opacity shared by every material (and no map overrides them): fold them in
             bool uni = s->n_objects > 0;
