@@ -423,6 +423,26 @@ def test_triangle_bvh_returns_the_leaf_walk_hits(name, jit, monkeypatch):
     assert np.array_equal(ab, a0)
 
 
+@pytest.mark.parametrize("name", ["CornellBox2", "Minecraft", "Mesh"])
+def test_pixel_to_lane_mapping_and_bvh_splits_do_not_change_the_image(name, monkeypatch):
+    """Schedule-only knobs: a warp renders an 8x4 tile or 32 pixels of a row (MRT_TILE), the BVH is split by
+    the surface-area heuristic or at the median (MRT_BVH_SAH).  RNG and accumulator are keyed by the pixel and
+    a BVH only narrows the candidate set, so the accumulated radiance must be identical BIT FOR BIT."""
+    r = load(name, (100, 60), 1.0)  # not a multiple of the 16x8 block: partial tiles at the right and bottom edges
+    ref = None
+    for tile, sah in (("1", "1"), ("0", "1"), ("1", "0")):
+        monkeypatch.setenv("MRT_TILE", tile)
+        monkeypatch.setenv("MRT_BVH_SAH", sah)
+        s = mrt.Sampler(device=0)
+        s.execute(r.scene, r.frame, r.rt, 3)
+        a = s.accum()[0]
+        assert np.isfinite(a).all() and a.max() > 0
+        if ref is None:
+            ref = a
+        else:
+            assert np.array_equal(a, ref), (tile, sah)
+
+
 def test_full_size_film_properties():
     """Size-independent properties at the headline film size (2160x2160), per kernel: a render is
     bit-reproducible and does not depend on how the passes are cut into calls or launches (the RNG is
