@@ -304,18 +304,8 @@ __device__ __forceinline__ bool tri_test(const DTri& tr, f3 o_rel /* ray.orig - 
     return true;
 }
 
-// Mesh leg of Renderer::intersect, rt.rs:740-772, over the flattened depth-3 octree: the root box
-// must be pierced (rt.rs:708-710), then every non-empty leaf the ray pierces contributes its triangle
-// list (rt.rs:707-723); entry = first minimum t, exit = last maximum t.  o_rel = object-space origin
-// minus instance pos.
-//
-// Two phases per chunk of 32 leaves, because the lanes of a warp pierce different leaves: (1) all
-// lanes slab-test the chunk's leaves in lockstep and keep a bit per pierced leaf; (2) every lane
-// walks ITS OWN pierced leaves and tests one triangle per iteration, so the warp runs for the
-// longest lane's candidate list, not for the union of all lanes' leaves (ncu on Mesh.json: the
-// leaf-major loop issued 2/3 of its instructions with <= 3 active lanes).  Candidate order per lane
-// is unchanged (leaf order, then list order), so the first-min / last-max tie rules hold.
-// Triangle-BVH form of the same test (DMesh::bvh_root).  The reference's result only depends on the SET of
+// Mesh leg of Renderer::intersect (rt.rs:740-772), triangle-BVH form (DMesh::bvh_root; the sequential walk of the
+// octree leaves it replaces follows below and stays as the reference the tests compare with).  The reference's result only depends on the SET of
 // candidates — every triangle listed by a pierced leaf — and, between equal t, on their order.  So instead of
 // walking every pierced leaf's list (Mesh.json: ~200 leaf slab tests + ~50 triangle tests per ray), a tight BVH
 // over the triangles finds the few triangles the ray actually hits, and each HIT is then checked for candidacy
@@ -414,6 +404,18 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
     return true;
 }
 
+// Mesh leg of Renderer::intersect, rt.rs:740-772, over the flattened depth-3 octree: the root box
+// must be pierced (rt.rs:708-710), then every non-empty leaf the ray pierces contributes its triangle
+// list (rt.rs:707-723); entry = first minimum t, exit = last maximum t.  o_rel = object-space origin
+// minus instance pos.
+//
+// Two phases per chunk of 32 leaves, because the lanes of a warp pierce different leaves: (1) all
+// lanes slab-test the chunk's leaves in lockstep and keep a bit per pierced leaf; (2) every lane
+// walks ITS OWN pierced leaves and tests one triangle per iteration, so the warp runs for the
+// longest lane's candidate list, not for the union of all lanes' leaves (ncu on Mesh.json: the
+// leaf-major loop issued 2/3 of its instructions with <= 3 active lanes).  Candidate order per lane
+// is unchanged (leaf order, then list order), so the first-min / last-max tie rules hold.
+// (Only taken when the mesh has no triangle BVH: MRT_NO_MESH_BVH, the bit-identity tests.)
 template <bool ANY, bool WANT_T1>
 __device__ __forceinline__ bool mesh_test(const SceneCommon& c, uint32_t mesh_id, f3 o_rel, f3 d,
                                           float* t0, float* t1, int* i0, int* i1) {
