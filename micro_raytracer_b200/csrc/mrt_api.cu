@@ -388,7 +388,7 @@ int mrt_create(mrt_ctx** out, int device, uint32_t workers, uint32_t n_dim) {
         return MRT_ERR_CUDA;
     }
     if (const char* s = std::getenv("MRT_TILE")) c->tiled = std::atoi(s) != 0;
-    if (const char* s = std::getenv("MRT_BVH_SAH")) g_bvh_sah = std::atoi(s) != 0;
+    { const char* s = std::getenv("MRT_BVH_SAH"); g_bvh_sah = s ? std::atoi(s) != 0 : true; }
     if (const char* s = std::getenv("MRT_SPP_PER_LAUNCH")) {
         const int v = std::atoi(s);
         if (v > 0) c->spp_per_launch = (uint32_t)v;
