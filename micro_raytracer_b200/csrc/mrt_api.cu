@@ -327,9 +327,23 @@ uint32_t bvh_build(std::vector<PrimBox>& prims, size_t begin, size_t end, std::v
     bounds(mid, end, rlo, rhi);
     const uint32_t l = bvh_build(prims, begin, mid, nodes, depth + 1, max_depth);
     const uint32_t r = bvh_build(prims, mid, end, nodes, depth + 1, max_depth);
+    // centre / half-extent form, left child in the low lane; the half extent is taken from the centre AS ROUNDED
+    // and padded, so the stored box still covers [lo, hi]
+    float cl[3], hl[3], cr[3], hr[3];
+    auto centre_half = [](const float* lo, const float* hi, float* c, float* h) {
+        for (int a = 0; a < 3; a++) {
+            c[a] = 0.5f * (lo[a] + hi[a]);
+            const float e = std::fmax(hi[a] - c[a], c[a] - lo[a]);
+            h[a] = e * (1.0f + 4e-7f) + 1e-30f;
+        }
+    };
+    centre_half(llo, lhi, cl, hl);
+    centre_half(rlo, rhi, cr, hr);
     BvhNode& n = (*nodes)[node];
-    n.llo = make_float4(llo[0], llo[1], llo[2], u2f(l)); n.lhi = make_float4(lhi[0], lhi[1], lhi[2], 0.0f);
-    n.rlo = make_float4(rlo[0], rlo[1], rlo[2], u2f(r)); n.rhi = make_float4(rhi[0], rhi[1], rhi[2], 0.0f);
+    n.q0 = make_float4(cl[0], cr[0], cl[1], cr[1]);
+    n.q1 = make_float4(cl[2], cr[2], hl[0], hr[0]);
+    n.q2 = make_float4(hl[1], hr[1], hl[2], hr[2]);
+    n.ref = make_uint4(l, r, 0u, 0u);
     return (uint32_t)node;
 }
 // world-space AABB of an object-space box of half extents h centred on pos, under world->object matrix M

@@ -70,10 +70,14 @@ static_assert(sizeof(FatInst) == 128, "FatInst must be one cache line");
 // primitive test as the brute-force loop and the winner is the lexicographic minimum of (t0, instance
 // index), i.e. exactly the brute-force result.  Children of an inner node are adjacent.
 // A node holds the boxes of BOTH its children, so one visit is one round of loads (the node's own box was
-// tested at its parent); llo.w / rlo.w (bits) = child reference: bit 31 set = leaf, the low bits are the
-// primitive (scene BVH: kind << 28 | index within the kind's table; mesh BVH: triangle index within the
-// mesh), else the index of the child node.  One primitive per leaf, so leaves need no node at all.
-struct BvhNode { float4 llo, lhi, rlo, rhi; };
+// tested at its parent).  The two boxes are stored like a BoxPair — centre / half extents, left child in the
+// low f32x2 lane, right child in the high one — so both slab intervals come out of 9 FFMA2 + 4 FMNMX3 with no
+// per-axis min/max (a lo/hi node costs 12 FFMA + 12 FMNMX + 4 FMNMX3, and the half-rate ALU pipe is what these
+// kernels wait for):  q0 = (cL.x, cR.x, cL.y, cR.y)  q1 = (cL.z, cR.z, hL.x, hR.x)  q2 = (hL.y, hR.y, hL.z, hR.z)
+// ref.x / ref.y = child references: bit 31 set = leaf, the low bits are the primitive (scene BVH: kind << 28 |
+// index within the kind's table; mesh BVH: triangle index within the mesh), else the index of the child node.
+// One primitive per leaf, so leaves need no node at all.
+struct BvhNode { float4 q0, q1, q2; uint4 ref; };
 #define MRT_BVH_LEAF 0x80000000u
 struct DLight { float4 v_kind; float4 color_pwr; };  // v.xyz (pos or unit -dir), w = kind bits ; color.rgb, pwr
 struct DTex { uint32_t w, h, first, has_dat; };      // texel offset into the float4 texel array
@@ -202,7 +206,28 @@ __device__ __forceinline__ f3 rcp_fixed3(f3 d) { return {rcp_fixed(d.x), rcp_fix
 // component becomes a huge finite slope (inside the slab -> (-huge, +huge), outside -> an empty interval)
 // instead of the reference's 1/E, which belongs to the primitive tests only.
 __device__ __forceinline__ f3 true_rcp3(f3 d, f3 m) {
-    return {d.x == 0.0f ? 1e30f : m.x, d.y == 0.0f ? 1e30f : m.y, d.z == 0.0f ? 1e30f : m.z};
+    // 1e18: huge against any ray parameter, small enough that (centre - origin) * slope cannot overflow
+    return {d.x == 0.0f ? 1e18f : m.x, d.y == 0.0f ? 1e18f : m.y, d.z == 0.0f ? 1e18f : m.z};
+}
+
+// Slab intervals (entry, exit) of the two children of a BVH node for a ray given as bm = true_rcp3 reciprocal,
+// bnom = -o * bm, bam = |bm| (mesh BVHs: o relative to the instance).
+struct NodeRay { f3 bm, bnom, bam; };
+__device__ __forceinline__ void node_slabs(const NodeRay& n, float4 q0, float4 q1, float4 q2,
+                                           float* tnl, float* tfl, float* tnr, float* tfr) {
+    const f2 cx = fma2(pk2(q0.x, q0.y), bc2(n.bm.x), bc2(n.bnom.x));
+    const f2 cy = fma2(pk2(q0.z, q0.w), bc2(n.bm.y), bc2(n.bnom.y));
+    const f2 cz = fma2(pk2(q1.x, q1.y), bc2(n.bm.z), bc2(n.bnom.z));
+    const f2 hx = pk2(q1.z, q1.w), hy = pk2(q2.x, q2.y), hz = pk2(q2.z, q2.w);
+    float lxa, lxb, lya, lyb, lza, lzb, hxa, hxb, hya, hyb, hza, hzb;
+    up2(fma2(hx, bc2(-n.bam.x), cx), lxa, lxb);
+    up2(fma2(hy, bc2(-n.bam.y), cy), lya, lyb);
+    up2(fma2(hz, bc2(-n.bam.z), cz), lza, lzb);
+    up2(fma2(hx, bc2(n.bam.x), cx), hxa, hxb);
+    up2(fma2(hy, bc2(n.bam.y), cy), hya, hyb);
+    up2(fma2(hz, bc2(n.bam.z), cz), hza, hzb);
+    *tnl = fmaxf(fmaxf(lxa, lya), lza); *tfl = fminf(fminf(hxa, hya), hza);
+    *tnr = fmaxf(fmaxf(lxb, lyb), lzb); *tfr = fminf(fminf(hxb, hyb), hzb);
 }
 
 // ------------------------------------------------------------------ RNG: pcg4d counter hash
@@ -293,13 +318,16 @@ __device__ __forceinline__ bool tri_test(const DTri& tr, f3 o_rel /* ray.orig - 
     if (det < MRT_E && det > -MRT_E) return false;
     float inv = frcp(det);
     f3 t = o_rel - xyz(tr.v0);
+    // The acceptance tests are written so that a NaN fails them (the reference's `if u < 0.0 || u > 1.0 { return None }`
+    // lets NaN through: a ray that comes back from 1e30 away — a grazing hit on an infinite plane — would "hit"
+    // every triangle with t = NaN).  For finite values the two forms are the same predicate.
     float u = dot(t, p) * inv;
-    if (u < 0.0f || u > 1.0f) return false;
+    if (!(u >= 0.0f && u <= 1.0f)) return false;
     f3 q = cross(t, e0);
     float v = dot(d, q) * inv;
-    if (v < 0.0f || (u + v) > 1.0f) return false;
+    if (!(v >= 0.0f && (u + v) <= 1.0f)) return false;
     float tt = dot(e1, q) * inv;
-    if (tt < 0.0f) return false;
+    if (!(tt >= 0.0f)) return false;
     *t_out = tt;
     return true;
 }
@@ -336,17 +364,10 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
         const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
         return !(tn > tf || tf < 0.0f);
     };
-    const f3 mb = true_rcp3(d, m);
-    const f3 omb = o_rel * mb;
-    auto slab = [&](float4 lo, float4 hi, float* tn_out) -> bool {
-        const float ax = fmaf(lo.x, mb.x, -omb.x), bx = fmaf(hi.x, mb.x, -omb.x);
-        const float ay = fmaf(lo.y, mb.y, -omb.y), by = fmaf(hi.y, mb.y, -omb.y);
-        const float az = fmaf(lo.z, mb.z, -omb.z), bz = fmaf(hi.z, mb.z, -omb.z);
-        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-        *tn_out = tn;
-        return !(tn > tf || tf < 0.0f);
-    };
+    NodeRay nr;
+    nr.bm = true_rcp3(d, m);
+    nr.bnom = mk(-o_rel.x * nr.bm.x, -o_rel.y * nr.bm.y, -o_rel.z * nr.bm.z);
+    nr.bam = mk(fabsf(nr.bm.x), fabsf(nr.bm.y), fabsf(nr.bm.z));
     constexpr bool PRUNE = !ANY && !WANT_T1;
     uint32_t cur = mh.bvh_root;
     for (;;) {
@@ -376,12 +397,13 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
                 }
             }
         } else {
-            const float4 llo = __ldg(&c.tbvh[cur].llo), lhi = __ldg(&c.tbvh[cur].lhi);
-            const float4 rlo = __ldg(&c.tbvh[cur].rlo), rhi = __ldg(&c.tbvh[cur].rhi);
-            float tl, tr;
-            bool hl = slab(llo, lhi, &tl), hr = slab(rlo, rhi, &tr);
+            const float4 q0 = __ldg(&c.tbvh[cur].q0), q1 = __ldg(&c.tbvh[cur].q1), q2 = __ldg(&c.tbvh[cur].q2);
+            const uint2 ref = __ldg(reinterpret_cast<const uint2*>(&c.tbvh[cur].ref));
+            float tl, tfl, tr, tfr;
+            node_slabs(nr, q0, q1, q2, &tl, &tfl, &tr, &tfr);
+            bool hl = !(tl > tfl || tfl < 0.0f), hr = !(tr > tfr || tfr < 0.0f);
             if (PRUNE) { hl = hl && tl <= b0; hr = hr && tr <= b0; }
-            const uint32_t cl = __float_as_uint(llo.w), cr = __float_as_uint(rlo.w);
+            const uint32_t cl = ref.x, cr = ref.y;
             if (hl && hr) {
                 const bool left_first = tl <= tr;
                 if (sp < 32) { stack[sp] = left_first ? cr : cl; stack_t[sp] = left_first ? tr : tl; sp++; }
@@ -545,7 +567,7 @@ __device__ __forceinline__ void best_update(Best& B, bool hit, float t0, float t
     }
 }
 
-struct RayPre { f3 o, d, m, nom, am, nam, bm, bnom; };  // m = 1/d (Box::intersect's fix-up applied), nom = -o*m, am = |m|, nam = -|m|; bm, bnom: true_rcp3 form for BVH nodes
+struct RayPre { f3 o, d, m, nom, am, nam; NodeRay n; };  // m = 1/d (Box::intersect's fix-up applied), nom = -o*m, am = |m|, nam = -|m|; bm, bnom: true_rcp3 form for BVH nodes
 
 // Box::intersect, rt.rs:299-333, centre/half form: n = (o - pos) m, k = half |m|,
 // t0 = max(-n - k), t1 = min(-n + k); miss iff t0 > t1 or t1 < 0.  Two boxes per call, one in
@@ -666,16 +688,6 @@ __device__ __forceinline__ void best_update_lex(Best& B, bool hit, float t0, flo
         }
     }
 }
-// slab interval of an AABB in the ray's parameter, same arithmetic as the primitive box test
-__device__ __forceinline__ bool node_hit(const RayPre& r, float4 lo, float4 hi, float best, float* tn_out) {
-    const float ax = fmaf(lo.x, r.bm.x, r.bnom.x), bx = fmaf(hi.x, r.bm.x, r.bnom.x);
-    const float ay = fmaf(lo.y, r.bm.y, r.bnom.y), by = fmaf(hi.y, r.bm.y, r.bnom.y);
-    const float az = fmaf(lo.z, r.bm.z, r.bnom.z), bz = fmaf(hi.z, r.bm.z, r.bnom.z);
-    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-    *tn_out = tn;
-    return tn <= tf && tf >= 0.0f && tn <= best;  // '<=': an equal t0 with a lower index must still be found
-}
 // The same interval with the primitive boxes' own arithmetic (r.m: the 1/E quirk included).  For a bracket
 // around AXIS-ALIGNED BOXES ONLY this is exactly monotone — every box interval computed with the same
 // formula lies inside its bracket's — so the specialised kernel's cluster brackets use this cheaper form.
@@ -768,12 +780,14 @@ __device__ __forceinline__ void bvh_traverse(Best& B, const GlobalScene& s, cons
             bvh_leaf<F, ANY, WANT_T1>(B, s, r, rp, cur & ~MRT_BVH_LEAF);
             if constexpr (ANY) { if (B.any) return; }
         } else {
-            const float4 llo = __ldg(&s.bvh[cur].llo), lhi = __ldg(&s.bvh[cur].lhi);
-            const float4 rlo = __ldg(&s.bvh[cur].rlo), rhi = __ldg(&s.bvh[cur].rhi);
-            float tl, tr;
-            const bool hl = node_hit(r, llo, lhi, B.t0, &tl);
-            const bool hr = node_hit(r, rlo, rhi, B.t0, &tr);
-            const uint32_t cl = __float_as_uint(llo.w), cr = __float_as_uint(rlo.w);
+            const float4 q0 = __ldg(&s.bvh[cur].q0), q1 = __ldg(&s.bvh[cur].q1), q2 = __ldg(&s.bvh[cur].q2);
+            const uint2 ref = __ldg(reinterpret_cast<const uint2*>(&s.bvh[cur].ref));
+            float tl, tfl, tr, tfr;
+            node_slabs(r.n, q0, q1, q2, &tl, &tfl, &tr, &tfr);
+            // '<=': an equal t0 with a lower index must still be found
+            const bool hl = tl <= tfl && tfl >= 0.0f && tl <= B.t0;
+            const bool hr = tr <= tfr && tfr >= 0.0f && tr <= B.t0;
+            const uint32_t cl = ref.x, cr = ref.y;
             if (hl && hr) {
                 const bool left_first = tl <= tr;
                 if (sp < 32) { stack[sp] = left_first ? cr : cl; stack_t[sp] = left_first ? tr : tl; sp++; }
@@ -814,8 +828,9 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
     r.nom = mk(-o.x * r.m.x, -o.y * r.m.y, -o.z * r.m.z);
     r.am = mk(fabsf(r.m.x), fabsf(r.m.y), fabsf(r.m.z));
     r.nam = -r.am;
-    r.bm = true_rcp3(d, r.m);  // only the node tests (scene BVH, cluster brackets) read these
-    r.bnom = mk(-o.x * r.bm.x, -o.y * r.bm.y, -o.z * r.bm.z);
+    r.n.bm = true_rcp3(d, r.m);  // only the BVH node tests read these
+    r.n.bnom = mk(-o.x * r.n.bm.x, -o.y * r.n.bm.y, -o.z * r.n.bm.z);
+    r.n.bam = mk(fabsf(r.n.bm.x), fabsf(r.n.bm.y), fabsf(r.n.bm.z));
     const RayPk rp = {pk2(o.x, d.x), pk2(o.y, d.y), pk2(o.z, d.z)};
     Best B;
     B.t0 = __int_as_float(0x7f800000); B.t1 = 0.0f; B.bi = -1; B.tr0 = B.tr1 = -1; B.any = false;
