@@ -140,6 +140,25 @@ def test_errors_use_the_reference_messages(tmp_path):
     assert json.loads(p.stdout)["scene"]["renderer"][0]["type"] == "sphere"
 
 
+def test_json_reader_and_verbose_dump_round_trip(tmp_path):
+    """The host's own JSON reader (stands in for serde_json): escapes, exponents, nesting, explicit nulls (serde
+    Option), key order kept; `-v` dumps the merged description, which must parse back to the same packing."""
+    src = tmp_path / "odd.json"
+    src.write_text('{ "rt" : {"bounce": 3, "sample": 2.0, "loss": 1.5e-1},\n "frame": {"res": [6.4e1, 48], "ssaa": 1, "cam": null},\n'
+                   ' "scene": {"renderer": [{"type": "sphere", "r": 5E-1, "name": "q\\"uo\\u0074e\\n", "mat": {"albedo": "#FF8000", "tex": null}},'
+                   ' {"type": "plane", "n": [0, 0, 1], "pos": [-0.0, 0, -1e0]}], "light": null, "sky": {"pwr": 0.25}}}')
+    p = run("--dry", "-v", src)
+    dumped = json.loads(p.stdout)
+    assert dumped["scene"]["renderer"][0]["name"] == 'q"uote\n' and list(dumped) == ["rt", "frame", "scene"]
+    back = tmp_path / "back.json"
+    back.write_text(p.stdout)
+    a, b = native_packed(tmp_path, src), native_packed(tmp_path, back)
+    assert a == b == packed_bytes(mrt.load_render(str(src)))
+    for bad in ('{"rt": {"bounce": 1} trailing', '{"rt": {"bounce": 01x}}', '{"rt": [1, 2,]}', '{"a": "\\q"}', ""):
+        src.write_text(bad)
+        assert run("--dry", src, check=False).returncode == 1, bad
+
+
 def test_image_encoders_round_trip(tmp_path):
     """PNG / PPM are lossless, JPEG decodes close to the source (stand-ins for the image crate at cli.rs:168,174, http.rs:122)."""
     from PIL import Image
@@ -246,7 +265,7 @@ def test_native_http_returns_the_rendered_jpeg(native_server):
     assert head.startswith(b"HTTP/1.1 200 OK") and b"Content-Type: image/jpeg" in head
     n = int([l for l in head.split(b"\r\n") if l.startswith(b"Content-Length")][0].split(b": ")[1])
     img = np.asarray(Image.open(io.BytesIO(payload[:n])).convert("RGB")).astype(np.float64)
-    r = mrt.render_from_dict(d) if hasattr(mrt, "render_from_dict") else __import__("micro_raytracer_b200.scene", fromlist=["x"]).render_from_dict(d)
+    r = mrt.render_from_dict(d)
     s = mrt.Sampler(device=0)
     s.execute(r.scene, r.frame, r.rt, 4)
     want = s.img(r.frame).astype(np.float64)
