@@ -18,6 +18,16 @@
  * are independent (the reference makes one Sampler per HTTP connection thread,
  * src/http.rs:138,155).
  *
+ * The reference's call pattern is the first-class one: Sampler::new once, then
+ * `for _ in 0..rt.sample { sampler.execute(&scene, &frame, &rt) }` and img()
+ * (src/cli.rs:157-174, src/http.rs:138-147).  A host that maps it literally —
+ * mrt_create_group(all devices) once; per pass mrt_update_scene, mrt_update_frame,
+ * mrt_set_rt, mrt_execute(ctx, 1, &t); mrt_img at the end or after any pass —
+ * gets every GPU of the box and full-length kernel launches: one-pass calls are
+ * queued and rendered in launches of up to spp_per_launch passes per device
+ * (MRT_OPT_COALESCE), the devices of a group split the samples, and mrt_img
+ * gathers their films over NVLink peer mappings.
+ *
  * There is NO CPU fallback behind this ABI: every entry point that computes
  * runs hand-written sm_100a CUDA kernels and fails with MRT_ERR_CUDA when no
  * device is usable.
@@ -32,7 +42,7 @@
 extern "C" {
 #endif
 
-#define MRT_ABI_VERSION 1
+#define MRT_ABI_VERSION 2
 
 typedef enum mrt_status {
     MRT_OK = 0,
@@ -138,6 +148,17 @@ typedef struct mrt_ctx mrt_ctx;
 /* ≙ Sampler::new(workers, n_dim), sampler.rs:19.  `workers`/`n_dim` (--worker/--dim) are
  * accepted for signature parity and ignored: the CUDA grid replaces the tile pool. */
 int mrt_create(mrt_ctx** out, int device, uint32_t workers, uint32_t n_dim);
+/* The same Sampler over SEVERAL devices of the box (devices == NULL or n_devices <= 0: all of them; at most 16).
+ * Every entry point below takes the group context like a plain one.  The group splits the passes of
+ * mrt_execute over its devices (pass k goes to device k mod G; the RNG is keyed by pixel and global sample
+ * index, so the image equals the one-device image up to the f32 summation order) and read-out (mrt_img,
+ * mrt_img_ss, mrt_accum) sums the devices' films: each device tone-maps one band of pixels, reading that band
+ * of every film over peer mappings (NVLink) and writing u8 pixels into the first device's image — no NCCL,
+ * no host staging.  Devices without peer access fall back to staged device-to-device copies.  One device in
+ * the list gives a plain context.  mrt_trace_primary, mrt_fp32_peak and mrt_set_stream act on the first device. */
+int mrt_create_group(mrt_ctx** out, const int* devices, int n_devices, uint32_t workers, uint32_t n_dim);
+/* Devices behind the context (1 for a plain one) and whether they map each other's memory. */
+int mrt_group_info(mrt_ctx* ctx, uint32_t* n_devices, uint32_t* peer_access);
 void mrt_destroy(mrt_ctx* ctx);
 const char* mrt_last_error(const mrt_ctx* ctx);   /* ctx may be NULL: last create error */
 int mrt_abi_version(void);
@@ -150,6 +171,13 @@ int mrt_device_count(int* n);
  * passes (the reference would have to build a new Sampler). */
 int mrt_set_scene(mrt_ctx* ctx, const mrt_scene* scene);
 int mrt_set_frame(mrt_ctx* ctx, const mrt_frame* frame);
+/* For hosts that, like Sampler::execute (sampler.rs:28), are handed scene and frame on EVERY pass: a
+ * description identical to the one the context holds (64-bit content hash of every array / memcmp of the
+ * frame) is a no-op that keeps the accumulated passes; anything else is mrt_set_scene / mrt_set_frame.
+ * (Deviation: the reference keeps adding into the same buffer when the scene changes between passes,
+ * sampler.rs:60-70 — here a changed scene or frame starts a new film.) */
+int mrt_update_scene(mrt_ctx* ctx, const mrt_scene* scene);
+int mrt_update_frame(mrt_ctx* ctx, const mrt_frame* frame);
 /* RayTracer{bounce, loss} (rt.rs:16-22).  `seed` keys the counter-based RNG that stands
  * in for rand::thread_rng (unseedable in the reference). */
 int mrt_set_rt(mrt_ctx* ctx, uint32_t bounce, float loss, uint64_t seed);
@@ -170,23 +198,37 @@ int mrt_set_rt(mrt_ctx* ctx, uint32_t bounce, float loss, uint64_t seed);
  *                    specialised kernel is ready.  A call of >= 2^33 paths waits for it.  Falls back to
  *                    the generic kernel if NVRTC is unavailable.
  *     MRT_JIT_OFF    never          MRT_JIT_FORCE   always, waiting for the compile (error if it fails).
- *                    Takes effect at the next mrt_execute. */
-typedef enum mrt_option { MRT_OPT_NORMAL_SPACE = 1, MRT_OPT_JIT = 2 } mrt_option;
+ *                    Takes effect at the next mrt_execute.
+ *   MRT_OPT_COALESCE       1 (default): mrt_execute(ctx, 1, ..) — the reference's one-pass call — only queues
+ *                          the pass; see mrt_execute.  0: every call launches and waits (env MRT_COALESCE). */
+typedef enum mrt_option { MRT_OPT_NORMAL_SPACE = 1, MRT_OPT_JIT = 2, MRT_OPT_COALESCE = 3 } mrt_option;
 enum { MRT_NORMAL_FORWARD_XF = 0, MRT_NORMAL_OBJECT = 1 };
 enum { MRT_JIT_OFF = 0, MRT_JIT_AUTO = 1, MRT_JIT_FORCE = 2 };
 int mrt_set_option(mrt_ctx* ctx, uint32_t option, uint32_t value);
 
-/* Multi-GPU sample split: this context renders global sample indices
- * rank, rank + world, rank + 2*world, ...  Default rank 0 of world 1. */
+/* Sample split across PROCESSES (one context or group per process, e.g. one rank per GPU under torchrun, or one
+ * group per node): this context renders global sample indices rank, rank + world, rank + 2*world, ...  Default
+ * rank 0 of world 1.  The devices of one process need no partition: use mrt_create_group. */
 int mrt_set_partition(mrt_ctx* ctx, uint32_t rank, uint32_t world);
 
-/* ≙ n_passes × Sampler::execute (sampler.rs:28-78): adds n_passes paths per supersampled
- * pixel to the accumulation buffer.  Blocks until the device is done; *seconds (optional)
- * receives the device time of the launches (CUDA events). */
+/* ≙ n_passes × Sampler::execute (sampler.rs:28-78): adds n_passes paths per supersampled pixel to the film.
+ *   n_passes == 1 (the reference's call, cli.rs:163 / http.rs:142; MRT_OPT_COALESCE on): the pass is QUEUED and the
+ *     call returns at once.  Queued passes are rendered spp_per_launch (per device) at a time, and whenever something
+ *     needs the film (mrt_img, mrt_img_ss, mrt_accum, mrt_accum_device, mrt_sync) or the settings they were asked
+ *     under change (mrt_set_rt, mrt_set_partition) — so the loop `for _ in 0..1024 { execute }; img()` runs the same
+ *     launches, bit for bit, as one mrt_execute(ctx, 1024, ..).  *seconds receives the AMORTISED device time: the
+ *     CUDA-event time of the launches that finished since the last report (0 while nothing finished), so the
+ *     per-pass log lines of cli.rs:164 still add up to the render time.
+ *   n_passes != 1: queued passes + these are launched and the call blocks until the device is done; *seconds
+ *     receives the device time not reported yet (for a group: the slowest device's).
+ * mrt_film_size counts queued passes as rendered. */
 int mrt_execute(mrt_ctx* ctx, uint32_t n_passes, double* seconds);
-/* Same, without waiting: the launches are queued on the context's stream. */
+/* Launch queued passes + n_passes without waiting: the launches are queued on the context's stream(s). */
 int mrt_execute_async(mrt_ctx* ctx, uint32_t n_passes);
+/* Launch what is queued and wait for the device(s). */
 int mrt_sync(mrt_ctx* ctx);
+/* Device seconds (CUDA events) of all path launches of this context that have finished, since mrt_create. */
+int mrt_device_seconds(mrt_ctx* ctx, double* total);
 
 /* Drop the accumulated passes (≙ a fresh Sampler). */
 int mrt_reset(mrt_ctx* ctx);
@@ -197,7 +239,8 @@ int mrt_film_size(mrt_ctx* ctx, uint32_t* nw, uint32_t* nh, uint32_t* passes);
 /* Linear accumulated sums, RGB f32, nw*nh*3 (what Sampler.colors holds, sampler.rs:14). */
 int mrt_accum(mrt_ctx* ctx, float* rgb, uint32_t* passes);
 /* Device view of the accumulator: nw*nh float4 (rgb + unused w), for an NCCL reduce by the
- * host (one process per GPU).  mrt_set_passes records the pass count the summed buffer holds. */
+ * host (one process per GPU).  mrt_set_passes records the pass count the summed buffer holds.
+ * A group first sums its devices' films onto its first device and hands that one out. */
 int mrt_accum_device(mrt_ctx* ctx, void** dptr, size_t* n_floats, void** cuda_stream);
 int mrt_set_passes(mrt_ctx* ctx, uint32_t passes);
 /* Run this context's work on a caller-owned CUDA stream (a cudaStream_t / CUstream handle, e.g.

@@ -5,6 +5,7 @@ layouts only — no library is loaded here.
 """
 import ctypes as C
 
+MRT_ABI_VERSION = 2
 MRT_OK, MRT_ERR_INVALID, MRT_ERR_CUDA, MRT_ERR_STATE, MRT_ERR_NOMEM = range(5)
 MRT_SPHERE, MRT_PLANE, MRT_BOX, MRT_TRIANGLE, MRT_MESH = range(5)
 MRT_LIGHT_POINT, MRT_LIGHT_DIR = range(2)
@@ -85,8 +86,9 @@ HIT_DTYPE = [
 
 # Every symbol include/mrt.h declares (tests check the built library exports all of them).
 MRT_SYMBOLS = [
-    "mrt_create", "mrt_destroy", "mrt_last_error", "mrt_abi_version",
-    "mrt_set_scene", "mrt_set_frame", "mrt_set_rt", "mrt_set_partition",
+    "mrt_create", "mrt_create_group", "mrt_group_info", "mrt_device_count", "mrt_destroy", "mrt_last_error", "mrt_abi_version",
+    "mrt_set_scene", "mrt_set_frame", "mrt_update_scene", "mrt_update_frame", "mrt_set_rt", "mrt_set_option", "mrt_set_partition",
+    "mrt_device_seconds", "mrt_spp_per_launch", "mrt_jit_status",
     "mrt_execute", "mrt_execute_async", "mrt_sync", "mrt_reset", "mrt_film_size",
     "mrt_accum", "mrt_accum_device", "mrt_set_passes", "mrt_set_stream", "mrt_img", "mrt_img_ss",
     "mrt_trace_primary", "mrt_launch_count", "mrt_fp32_peak",

@@ -10,9 +10,10 @@ struct MrtJitInfo { bool pending = false; bool from_disk = false; double seconds
 
 // The kernel specialised for `scene_header` (the text mrt_api.cu generates: feature mask + instance
 // tables as literal X-macro lists).  The first request starts an NVRTC compile on a background thread
-// (or loads the cubin from the on-disk cache); wait = true blocks until it is over.  Returns nullptr
+// (or loads the cubin from the on-disk cache); wait_ms < 0 blocks until it is over, wait_ms > 0 waits at most that
+// long (a cubin found in the on-disk cache is ready within ~3 ms), 0 only polls.  Returns nullptr
 // while the compile is pending, when NVRTC is unavailable, or when the compile failed (info->err).
-cudaKernel_t mrt_jit_kernel(const std::string& scene_header, bool wait, MrtJitInfo* info);
+cudaKernel_t mrt_jit_kernel(const std::string& scene_header, int wait_ms, MrtJitInfo* info);
 // Blocks until a compile started for `scene_header` (if any) is over.
 void mrt_jit_wait(const std::string& scene_header);
 cudaError_t mrt_jit_launch(cudaKernel_t k, const SceneCommon& scene, const FilmParams& fp, cudaStream_t st);

@@ -93,6 +93,59 @@ __global__ void __launch_bounds__(256) tonemap_kernel(const float4* __restrict__
     out[3 * i + 2] = tonemap1(a.z, inv_n, gamma, e2);
 }
 
+// Device groups (mrt_create_group): the film of a group is the SUM of its members' accumulators.  Each member
+// tone-maps one band of pixels: it reads that band from every member's accumulator — its own from HBM, the others'
+// over NVLink peer mappings — adds them in member order (so the result does not depend on which device runs the
+// band) and writes the u8 pixels straight into the first member's supersampled image.  This is the group's only
+// exchange step: a gather fused into the film kernel instead of a reduce of the whole 16-byte-per-pixel buffer
+// followed by a tonemap.  Four pixels per thread: 4 x 16-byte loads per member, 12 bytes out as three 32-bit stores.
+__global__ void __launch_bounds__(256) tonemap_peers_kernel(const PeerAccums acc, uint8_t* __restrict__ out, uint32_t first, uint32_t count,
+                                                            float inv_n, float gamma, float e2) {
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (q >= count) return;
+    const uint32_t n = min(4u, count - q);
+    const uint32_t pix = first + q;
+    uint8_t b[12];
+    for (uint32_t k = 0; k < 4u; k++) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < n)
+            for (uint32_t m = 0; m < acc.n; m++) {
+                const float4 a = acc.p[m][pix + k];
+                s.x += a.x; s.y += a.y; s.z += a.z;
+            }
+        b[3 * k + 0] = tonemap1(s.x, inv_n, gamma, e2);
+        b[3 * k + 1] = tonemap1(s.y, inv_n, gamma, e2);
+        b[3 * k + 2] = tonemap1(s.z, inv_n, gamma, e2);
+    }
+    uint8_t* o = out + 3 * (size_t)pix;
+    if (n == 4u && (reinterpret_cast<uintptr_t>(o) & 3u) == 0u) {
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
+        for (int k = 0; k < 3; k++) o32[k] = (uint32_t)b[4 * k] | (uint32_t)b[4 * k + 1] << 8 | (uint32_t)b[4 * k + 2] << 16 | (uint32_t)b[4 * k + 3] << 24;
+    } else {
+        for (uint32_t k = 0; k < 3u * n; k++) o[k] = b[k];
+    }
+}
+// sum of the members' accumulators as packed RGB f32 (mrt_accum of a group)
+__global__ void __launch_bounds__(256) unpack_peers_kernel(const PeerAccums acc, float* __restrict__ out, uint32_t npix) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t m = 0; m < acc.n; m++) {
+        const float4 a = acc.p[m][i];
+        s.x += a.x; s.y += a.y; s.z += a.z;
+    }
+    out[3 * i] = s.x; out[3 * i + 1] = s.y; out[3 * i + 2] = s.z;
+}
+// dst += src (src: a peer's accumulator through its P2P mapping, or a staged copy of it)
+__global__ void __launch_bounds__(256) accum_add_kernel(float4* __restrict__ dst, const float4* __restrict__ src, uint32_t npix) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    float4 d = dst[i];
+    const float4 a = src[i];
+    d.x += a.x; d.y += a.y; d.z += a.z;
+    dst[i] = d;
+}
+
 // image 0.24 imageops::resize(.., Lanczos3) (sampler.rs:98): per output index the window
 // [left, right) and its normalised weights.  One thread per output index; table row stride = max_taps.
 __device__ __forceinline__ float sinc_(float t) {
@@ -229,6 +282,22 @@ cudaError_t mrt_launch_primary(const GlobalScene& gs, const FilmParams& fp, mrt_
 cudaError_t mrt_launch_tonemap(const float4* accum, uint8_t* out, uint32_t npix, float inv_n, float gamma, float exp, cudaStream_t st) {
     const float d = 1.0f - exp;
     tonemap_kernel<<<(npix + 255) / 256, 256, 0, st>>>(accum, out, npix, inv_n, gamma, d * d);
+    return cudaGetLastError();
+}
+
+cudaError_t mrt_launch_tonemap_peers(const PeerAccums& acc, uint8_t* out, uint32_t first, uint32_t count, float inv_n, float gamma, float exp, cudaStream_t st) {
+    if (!count) return cudaSuccess;
+    const float d = 1.0f - exp;
+    const uint32_t threads = (count + 3u) / 4u;
+    tonemap_peers_kernel<<<(threads + 255) / 256, 256, 0, st>>>(acc, out, first, count, inv_n, gamma, d * d);
+    return cudaGetLastError();
+}
+cudaError_t mrt_launch_unpack_peers(const PeerAccums& acc, float* out, uint32_t npix, cudaStream_t st) {
+    unpack_peers_kernel<<<(npix + 255) / 256, 256, 0, st>>>(acc, out, npix);
+    return cudaGetLastError();
+}
+cudaError_t mrt_launch_accum_add(float4* dst, const float4* src, uint32_t npix, cudaStream_t st) {
+    accum_add_kernel<<<(npix + 255) / 256, 256, 0, st>>>(dst, src, npix);
     return cudaGetLastError();
 }
 

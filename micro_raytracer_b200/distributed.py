@@ -26,17 +26,30 @@ def reduce_accum(sampler, total_passes: int, group=None, dst: int = 0, device_te
     holds `total_passes` passes.
 
     device_tensor: a torch CUDA tensor aliasing the sampler's device accumulator
-    (torch.as_tensor(sampler.accum_device()[0], device=...)); the reduce then runs in place on
-    the device, ordered on the sampler's stream.  Without it the host accumulator
-    (sampler.accum()) is reduced and the sum is returned on `dst` (None elsewhere)."""
+    (torch.as_tensor(sampler.accum_device()[0], device=...)); the reduce then runs in place on the device.
+    Ordering: when the sampler was bound to torch's current stream (sampler.set_stream(stream.cuda_stream),
+    what bench.py does) the path kernels, the reduce and the later film kernels are ordered by that one
+    stream and nothing waits on the host.  Otherwise the sampler's kernels run on the context's private
+    stream, which torch knows nothing about: the sampler is synchronised before the reduce and torch's
+    stream after it, so the reduce never reads a film that is still being written and img() never
+    tone-maps one the reduce has not finished.
+    Without a device tensor the host accumulator (sampler.accum()) is reduced and the sum is returned on
+    `dst` (None elsewhere)."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     if device_tensor is not None:
+        cur = torch.cuda.current_stream(device_tensor.device)
+        shared = sampler.stream is not None and sampler.stream == cur.cuda_stream
+        sampler.accum_device()          # launches whatever passes are still queued in the library
+        if not shared:
+            sampler.sync()
         if world > 1:
             dist.reduce(device_tensor, dst=dst, op=dist.ReduceOp.SUM, group=group)
+        if not shared:
+            cur.synchronize()
         sampler.set_passes(total_passes)
         return None
     acc, _ = sampler.accum()

@@ -480,7 +480,7 @@ std::string usage() {
            "      --light ...        point: <f32 x3> | dir: <f32 x3>  pwr: col:\n"
            "      --sky r g b pwr    Scene sky color\n"
            "      --device N         CUDA device (extension)\n"
-           "      --gpus N           render on N GPUs, devices N.. from --device: sample split + one NCCL reduce (extension);\n"
+           "      --gpus N           one Sampler over N GPUs (devices --device .. +N-1): sample split, films gathered over NVLink (extension);\n"
            "                         with --http: requests go round-robin over the N GPUs\n"
            "      --seed N           RNG seed (extension: the reference is unseedable)\n";
 }

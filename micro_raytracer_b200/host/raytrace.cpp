@@ -9,41 +9,30 @@
 
 #include "http.hpp"
 #include "image_io.hpp"
-#include "multi.hpp"
 #include "parser.hpp"
 
 using namespace mrt_host;
 
 static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-// CLI::raytrace, cli.rs:155-177: one Sampler, rt.sample passes, optional save per pass, final save
+// CLI::raytrace, cli.rs:155-177, as the reference writes it: one Sampler, `rt.sample` one-pass calls, optional
+// save per pass (--update), final save.  The library queues the one-pass calls and renders them in full-length
+// launches, on every GPU of --gpus (one Sampler over a device group), so this loop IS the fast path.
 static double raytrace(const CliArgs& a, const Render& render, const Logger& log) {
-    const std::string out_name = a.output.value_or("out.png");
-    if (a.gpus > 1 && !a.update) {  // one image on several GPUs; --update shows every pass and stays on one GPU
-        std::vector<int> devices;
-        for (int g = 0; g < a.gpus; g++) devices.push_back(a.device + g);
-        MultiSampler multi(devices, (uint32_t)a.worker.value_or(24), (uint32_t)a.dim.value_or(64), a.seed);
-        const double t0 = now();
-        const double dt = multi.execute(render.scene, render.frame, render.rt, render.rt.sample);
-        if (log) log("cli:sample:0.." + std::to_string(render.rt.sample) + " on " + std::to_string(a.gpus) + " gpus: " + std::to_string(dt) + "s");
-        save_image(multi.img(render.frame), out_name);
-        return now() - t0;
-    }
-    Sampler sampler((uint32_t)a.worker.value_or(24), (uint32_t)a.dim.value_or(64), a.device, a.seed);
     const std::string out = a.output.value_or("out.png");
+    std::vector<int> devices;
+    for (int g = 0; g < a.gpus; g++) devices.push_back(a.device + g);
+    Sampler sampler(devices, (uint32_t)a.worker.value_or(24), (uint32_t)a.dim.value_or(64), a.seed);  // cli.rs:157
+    if (log && a.gpus > 1) log("cli:sampler: on " + std::to_string(sampler.n_devices()) + " gpus");
     const double t0 = now();
-    if (a.update) {
-        for (uint32_t n = 0; n < render.rt.sample; n++) {
-            const double dt = sampler.execute(render.scene, render.frame, render.rt);
-            if (log) log("cli:sample:" + std::to_string(n) + ": " + std::to_string(dt) + "s");
-            save_image(sampler.img(render.frame), out);
-        }
-    } else if (render.rt.sample > 0) {
-        // without --update nothing observes the accumulator between passes: one call renders them all
-        const double dt = sampler.execute(render.scene, render.frame, render.rt, render.rt.sample);
-        if (log) log("cli:sample:0.." + std::to_string(render.rt.sample - 1) + ": " + std::to_string(dt) + "s");
+    for (uint32_t n = 0; n < render.rt.sample; n++) {  // cli.rs:162
+        const double dt = sampler.execute(render.scene, render.frame, render.rt);
+        if (log) log("cli:sample:" + std::to_string(n) + ": " + std::to_string(dt) + "s");
+        if (a.update) save_image(sampler.img(render.frame), out);  // cli.rs:166-169
     }
-    save_image(sampler.img(render.frame), out);
+    const Image im = sampler.img(render.frame);  // cli.rs:173: renders whatever is still queued
+    if (log) log("cli:device: " + std::to_string(sampler.device_seconds()) + "s in path kernels");
+    save_image(im, out);
     return now() - t0;
 }
 

@@ -114,12 +114,24 @@ std::string PackedScene::bytes() const {
 }
 
 // ----------------------------------------------------------------------------- Sampler
+int cuda_device_count() {
+    int n = 0;
+    mrt_device_count(&n);
+    return n;
+}
+
 Sampler::Sampler(uint32_t workers, uint32_t n_dim, int device, uint64_t seed) : seed_(seed) {
     if (mrt_abi_version() != MRT_ABI_VERSION) throw Error("libmrt.so ABI version mismatch");
-    if (int rc = mrt_create(&ctx_, device, workers, n_dim)) {
-        (void)rc;
+    if (mrt_create(&ctx_, device, workers, n_dim)) {
         const char* e = mrt_last_error(nullptr);
         throw Error(e && *e ? e : "mrt_create failed");
+    }
+}
+Sampler::Sampler(const std::vector<int>& devices, uint32_t workers, uint32_t n_dim, uint64_t seed) : seed_(seed) {
+    if (mrt_abi_version() != MRT_ABI_VERSION) throw Error("libmrt.so ABI version mismatch");
+    if (mrt_create_group(&ctx_, devices.empty() ? nullptr : devices.data(), (int)devices.size(), workers, n_dim)) {
+        const char* e = mrt_last_error(nullptr);
+        throw Error(e && *e ? e : "mrt_create_group failed");
     }
 }
 Sampler::~Sampler() {
@@ -132,28 +144,15 @@ void Sampler::check(int rc, const char* what) {
     }
 }
 void Sampler::set_option(uint32_t option, uint32_t value) {
-    check(mrt_set_option(ctx_, option, value), "mrt_set_option");
-    scene_key_.clear();  // options take effect at the next mrt_set_scene
+    check(mrt_set_option(ctx_, option, value), "mrt_set_option");  // the scene hash covers the options: re-sent when needed
 }
 void Sampler::bind(const Scene& scene, const Frame& frame, const RayTracer& rt) {
-    PackedScene packed(scene);
-    std::string sk = packed.bytes();
-    if (sk != scene_key_ || scene_key_.empty()) {
-        check(mrt_set_scene(ctx_, &packed.c()), "mrt_set_scene");
-        scene_key_ = std::move(sk);
-    }
-    mrt_frame f = frame.pack();
-    std::string fk(reinterpret_cast<const char*>(&f), sizeof f);
-    if (fk != frame_key_) {
-        check(mrt_set_frame(ctx_, &f), "mrt_set_frame");
-        frame_key_ = std::move(fk);
-    }
-    std::string rk(reinterpret_cast<const char*>(&rt.bounce), 4);
-    rk.append(reinterpret_cast<const char*>(&rt.loss), 4);
-    if (rk != rt_key_) {
-        check(mrt_set_rt(ctx_, rt.bounce, rt.loss, seed_), "mrt_set_rt");
-        rt_key_ = std::move(rk);
-    }
+    const PackedScene packed(scene);
+    check(mrt_update_scene(ctx_, &packed.c()), "mrt_update_scene");
+    const mrt_frame f = frame.pack();
+    check(mrt_update_frame(ctx_, &f), "mrt_update_frame");
+    have_frame_ = true;
+    check(mrt_set_rt(ctx_, rt.bounce, rt.loss, seed_), "mrt_set_rt");
 }
 double Sampler::execute(const Scene& scene, const Frame& frame, const RayTracer& rt, uint32_t n_passes) {
     bind(scene, frame, rt);
@@ -162,10 +161,10 @@ double Sampler::execute(const Scene& scene, const Frame& frame, const RayTracer&
     return sec;
 }
 Image Sampler::img(const Frame& frame) {
-    if (frame_key_.empty()) {
-        mrt_frame f = frame.pack();
-        check(mrt_set_frame(ctx_, &f), "mrt_set_frame");
-        frame_key_.assign(reinterpret_cast<const char*>(&f), sizeof f);
+    if (!have_frame_) {
+        const mrt_frame f = frame.pack();
+        check(mrt_update_frame(ctx_, &f), "mrt_update_frame");
+        have_frame_ = true;
     }
     Image im;
     im.w = frame.res[0]; im.h = frame.res[1];
@@ -177,6 +176,17 @@ uint32_t Sampler::passes() {
     uint32_t nw = 0, nh = 0, p = 0;
     check(mrt_film_size(ctx_, &nw, &nh, &p), "mrt_film_size");
     return p;
+}
+uint32_t Sampler::n_devices() {
+    uint32_t n = 1;
+    check(mrt_group_info(ctx_, &n, nullptr), "mrt_group_info");
+    return n;
+}
+void Sampler::sync() { check(mrt_sync(ctx_), "mrt_sync"); }
+double Sampler::device_seconds() {
+    double t = 0.0;
+    check(mrt_device_seconds(ctx_, &t), "mrt_device_seconds");
+    return t;
 }
 
 }  // namespace mrt_host

@@ -130,28 +130,41 @@ struct Image {  // ≙ image::RgbImage
 
 // ≙ `Sampler` of src/sampler.rs.  `workers` / `n_dim` (--worker / --dim, cli.rs:157) are accepted
 // and ignored by the library: the CUDA grid replaces the tile pool.
+// The reference's call pattern is the intended one: construct once, `execute(scene, frame, rt)` once per
+// pass, `img(frame)` whenever an image is wanted.  One-pass calls are queued inside the library and
+// rendered in full-length launches; a Sampler over several devices (second constructor: mrt_create_group)
+// splits the samples over them and gathers the films over NVLink peer mappings in img().
 class Sampler {
 public:
     Sampler(uint32_t workers = 24, uint32_t n_dim = 64, int device = 0, uint64_t seed = 0x5EED);
+    // one Sampler over several GPUs of the box; an empty list means all of them
+    Sampler(const std::vector<int>& devices, uint32_t workers = 24, uint32_t n_dim = 64, uint64_t seed = 0x5EED);
     ~Sampler();
     Sampler(const Sampler&) = delete;
     Sampler& operator=(const Sampler&) = delete;
 
-    // ≙ n_passes × Sampler::execute (sampler.rs:28); returns the device seconds of the launches.
-    // scene / frame / rt are borrowed for the call and re-uploaded only when they changed.
+    // ≙ n_passes × Sampler::execute (sampler.rs:28); returns device seconds (a one-pass call: the amortised time
+    // of the launches that finished since the last call).  scene / frame / rt are borrowed for the call as in the
+    // reference — nothing is cached on this side: they are packed and handed over every time, and the library
+    // re-uploads only when the CONTENT changed (mrt_update_scene / mrt_update_frame).
     double execute(const Scene& scene, const Frame& frame, const RayTracer& rt, uint32_t n_passes = 1);
     Image img(const Frame& frame);          // ≙ Sampler::img (sampler.rs:80-99)
     void set_option(uint32_t option, uint32_t value);
     uint32_t passes();
+    uint32_t n_devices();
+    void sync();                 // launch what is queued and wait for the device(s)
+    double device_seconds();     // CUDA-event seconds of every finished path launch
     mrt_ctx* ctx() { return ctx_; }
-    // upload what changed of the three borrows (what execute does first); for hosts that queue work themselves
+    // hand over the three borrows (what execute does first); for hosts that queue work themselves
     void bind(const Scene& scene, const Frame& frame, const RayTracer& rt);
 
 private:
     void check(int rc, const char* what);
     mrt_ctx* ctx_ = nullptr;
     uint64_t seed_;
-    std::string scene_key_, frame_key_, rt_key_;
+    bool have_frame_ = false;
 };
+
+int cuda_device_count();  // via libmrt.so; 0 without a driver
 
 }  // namespace mrt_host

@@ -16,6 +16,7 @@ import threading
 import time
 from typing import Optional, Tuple
 
+from .sampler import MrtError
 from .scene import SceneError, render_from_dict
 
 MAX_REQUEST = 1024 * 1024  # http.rs:66: one read into a 1 MiB buffer
@@ -28,15 +29,17 @@ def render_jpeg(body: bytes, device: int = 0, log=None) -> bytes:
     from .sampler import Sampler
     render = render_from_dict(json.loads(body.decode("utf-8")))
     sampler = Sampler(24, 64, device=device)  # http.rs:138
-    t0 = time.perf_counter()
-    if render.rt.sample > 0:
-        sampler.execute(render.scene, render.frame, render.rt, render.rt.sample)
-    img = sampler.img(render.frame)
-    if log:
-        log(f"http:done: {time.perf_counter() - t0:.3f}s")
+    try:  # the context and its device buffers go away whatever happens below
+        t0 = time.perf_counter()
+        if render.rt.sample > 0:
+            sampler.execute(render.scene, render.frame, render.rt, render.rt.sample)
+        img = sampler.img(render.frame)
+        if log:
+            log(f"http:done: {time.perf_counter() - t0:.3f}s")
+    finally:
+        sampler.close()
     buf = io.BytesIO()
     Image.fromarray(img).save(buf, format="JPEG", quality=90)
-    sampler.close()
     return buf.getvalue()
 
 
@@ -92,7 +95,7 @@ class _Handler(socketserver.BaseRequestHandler):
                 return self._status("400 Bad Request")
             try:
                 jpg = render_jpeg(body, self.device, self.log)
-            except (SceneError, ValueError, KeyError, TypeError) as e:
+            except (SceneError, MrtError, ValueError, KeyError, TypeError) as e:  # MrtError: what the library rejects
                 if self.log:
                     self.log(f"http: {e}")
                 return self._status("400 Bad Request")

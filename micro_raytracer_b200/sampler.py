@@ -4,6 +4,11 @@
     dt = sampler.execute(scene, frame, rt)         # ≙ Sampler::execute  sampler.rs:28 (one pass)
     img = sampler.img(frame)                       # ≙ Sampler::img      sampler.rs:80
 
+`Sampler(devices=[0, 1, ...])` (or `devices="all"`) is the same object over several GPUs of the box
+(mrt_create_group): the passes are split over the devices inside the library and `img()` gathers their
+films over NVLink peer mappings.  One-pass `execute` calls — the reference's loop — are queued by the
+library and rendered in full-length launches (include/mrt.h: mrt_execute).
+
 exactly as CLI::raytrace drives it (src/cli.rs:155-177).  All computation happens in the
 CUDA library `libmrt.so` (csrc/, built by __graft_entry__.build()); there is no CPU
 fallback — a missing library or device raises.
@@ -22,6 +27,7 @@ from .scene import Frame, PackedScene, RayTracer, Scene, pack_scene
 _LIB_NAME = "libmrt.so"
 OPT_NORMAL_SPACE, NORMAL_FORWARD_XF, NORMAL_OBJECT = 1, 0, 1  # include/mrt.h
 OPT_JIT, JIT_OFF, JIT_AUTO, JIT_FORCE = 2, 0, 1, 2
+OPT_COALESCE = 3
 _lib = None
 
 
@@ -60,6 +66,12 @@ def declare(lib, prefix: str = "mrt_"):
     fn("trace_primary", P, C.c_void_p)
     if prefix == "mrt_":
         fn("abi_version")
+        fn("create_group", C.POINTER(P), C.POINTER(C.c_int), C.c_int, u32, u32)
+        fn("group_info", P, C.POINTER(u32), C.POINTER(u32))
+        fn("device_count", C.POINTER(C.c_int))
+        fn("update_scene", P, C.POINTER(abi.MrtScene))
+        fn("update_frame", P, C.POINTER(abi.MrtFrame))
+        fn("device_seconds", P, C.POINTER(C.c_double))
         fn("execute_async", P, u32)
         fn("sync", P)
         fn("accum_device", P, C.POINTER(P), C.POINTER(C.c_size_t), C.POINTER(P))
@@ -81,7 +93,7 @@ def load_library():
             raise MrtError(f"{p} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(there is no CPU fallback)")
         _lib = declare(C.CDLL(p))
-        if _lib.mrt_abi_version() != 1:
+        if _lib.mrt_abi_version() != abi.MRT_ABI_VERSION:
             raise MrtError("libmrt.so ABI version mismatch")
     return _lib
 
@@ -100,10 +112,14 @@ class Sampler:
 
     prefix = "mrt_"
 
-    def __init__(self, workers: int = 24, n_dim: int = 64, device: int = 0, seed: int = 0x5EED, _lib=None):
+    def __init__(self, workers: int = 24, n_dim: int = 64, device: int = 0, seed: int = 0x5EED, _lib=None, devices=None):
         self._lib = _lib if _lib is not None else load_library()
         self._ctx = C.c_void_p()
-        self._create(workers, n_dim, device)
+        self._stream = None
+        if devices is not None:
+            self._create_group(workers, n_dim, devices)
+        else:
+            self._create(workers, n_dim, device)
         self.seed = seed
         self._scene_key = None
         self._frame_key = None
@@ -118,6 +134,21 @@ class Sampler:
         rc = self._lib.mrt_create(C.byref(self._ctx), int(device), int(workers), int(n_dim))
         if rc:
             raise MrtError((self._lib.mrt_last_error(None) or b"mrt_create failed").decode())
+
+    def _create_group(self, workers, n_dim, devices):
+        """devices: a list of CUDA device indices, or "all"."""
+        if isinstance(devices, str):
+            if devices != "all":
+                raise ValueError("devices must be a list of device indices or 'all'")
+            arr, n = None, 0
+        else:
+            devices = [int(d) for d in devices]
+            arr, n = (C.c_int * len(devices))(*devices), len(devices)
+            if n == 0:
+                raise ValueError("empty device list")
+        rc = self._lib.mrt_create_group(C.byref(self._ctx), arr, n, int(workers), int(n_dim))
+        if rc:
+            raise MrtError((self._lib.mrt_last_error(None) or b"mrt_create_group failed").decode())
 
     def _check(self, rc):
         if rc:
@@ -155,14 +186,18 @@ class Sampler:
     def set_partition(self, rank: int, world: int):
         self._check(self._f("set_partition")(self._ctx, int(rank), int(world)))
 
+    @staticmethod
+    def _key_of(frame: Frame):
+        return (tuple(frame.res), frame.ssaa, tuple(frame.cam.pos), tuple(frame.cam.dir), frame.cam.fov,
+                frame.cam.gamma, frame.cam.exp, frame.cam.aprt, frame.cam.foc)
+
     def _bind(self, scene, frame: Frame, rt: RayTracer):
         sk = id(scene)
         if sk != self._scene_key:
             self.set_scene(scene)
             self._scene_key = sk
             self._scene_ref = scene
-        fk = (tuple(frame.res), frame.ssaa, tuple(frame.cam.pos), tuple(frame.cam.dir), frame.cam.fov,
-              frame.cam.gamma, frame.cam.exp, frame.cam.aprt, frame.cam.foc)
+        fk = self._key_of(frame)
         if fk != self._frame_key:
             self.set_frame(frame)
             self._frame_key = fk
@@ -173,7 +208,8 @@ class Sampler:
 
     # -- the reference API
     def execute(self, scene, frame: Frame, rt: RayTracer, n_passes: int = 1) -> float:
-        """One pass (or n_passes) = one path per supersampled pixel; returns seconds."""
+        """One pass (or n_passes) = one path per supersampled pixel; returns device seconds (for a
+        one-pass call: the amortised time of the launches that finished since the last call)."""
         self._bind(scene, frame, rt)
         sec = C.c_double()
         self._check(self._f("execute")(self._ctx, int(n_passes), C.byref(sec)))
@@ -183,6 +219,7 @@ class Sampler:
         """(res_h, res_w, 3) uint8, ≙ Sampler::img."""
         if frame is not None and self._frame_key is None:
             self.set_frame(frame)
+            self._frame_key = self._key_of(frame)
         w, h = self._res
         out = np.empty((h, w, 3), np.uint8)
         self._check(self._f("img")(self._ctx, out.ctypes.data_as(C.POINTER(C.c_uint8))))
@@ -240,6 +277,43 @@ class Sampler:
     def set_stream(self, cuda_stream: Optional[int]):
         """Queue this sampler's work on a caller-owned stream (e.g. torch's current stream)."""
         self._check(self._lib.mrt_set_stream(self._ctx, C.c_void_p(cuda_stream or 0)))
+        self._stream = cuda_stream or None
+
+    @property
+    def stream(self) -> Optional[int]:
+        """The caller-owned stream handle set with set_stream (None: the context's private stream)."""
+        return self._stream
+
+    def update_scene(self, packed: PackedScene):
+        """mrt_update_scene: a no-op when the context already holds this very content (keeps the passes)."""
+        self._check(self._lib.mrt_update_scene(self._ctx, C.byref(packed.c)))
+        self._packed = packed
+
+    def update_frame(self, frame: Frame):
+        f = frame.pack()
+        self._check(self._lib.mrt_update_frame(self._ctx, C.byref(f)))
+        self._frame_key = self._key_of(frame)
+
+    def pass_fn(self):
+        """The reference's per-pass call with the Python overhead stripped: returns a zero-argument callable that
+        is `mrt_execute(ctx, 1, NULL)` (scene, frame and rt must already be bound).  For host loops that call it
+        a thousand times per image (bench.py's e2e leg)."""
+        f, ctx = self._lib.mrt_execute, self._ctx
+
+        def one_pass():
+            if f(ctx, 1, None):
+                self._check(1)
+        return one_pass
+
+    def device_seconds(self) -> float:
+        t = C.c_double()
+        self._check(self._lib.mrt_device_seconds(self._ctx, C.byref(t)))
+        return t.value
+
+    def group_info(self) -> dict:
+        n, p = C.c_uint32(), C.c_uint32()
+        self._check(self._lib.mrt_group_info(self._ctx, C.byref(n), C.byref(p)))
+        return {"n_devices": n.value, "peer_access": bool(p.value)}
 
     def set_passes(self, passes: int):
         self._check(self._lib.mrt_set_passes(self._ctx, int(passes)))

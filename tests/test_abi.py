@@ -20,11 +20,12 @@ def _declared(header):
 def test_libmrt_exports_every_declared_symbol():
     lib = ctypes.CDLL(mrt.lib_path())
     names = _declared("include/mrt.h")
-    assert len(names) >= 23
+    assert len(names) >= 30
     for n in names:
         assert hasattr(lib, n), f"libmrt.so does not export {n}"
     lib.mrt_abi_version.restype = ctypes.c_int
-    assert lib.mrt_abi_version() == 1
+    assert lib.mrt_abi_version() == abi.MRT_ABI_VERSION == 2
+    assert set(abi.MRT_SYMBOLS) == set(names)
 
 
 def test_oracle_exports_every_declared_symbol():

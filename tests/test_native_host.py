@@ -280,8 +280,9 @@ def _n_devices():
 
 @pytest.mark.gpu
 def test_native_multi_gpu_render_equals_the_single_gpu_one(tmp_path):
-    """--gpus N: sample split over N devices + one ncclReduce of the accumulators (host/multi.cpp).
-    The counter-based RNG keys on the global sample index, so only the f32 summation order differs."""
+    """--gpus N: ONE Sampler over a device group (mrt_create_group): the library splits the samples over the
+    N devices and img() gathers their films over peer mappings.  The counter-based RNG keys on the global sample
+    index, so only the f32 summation order differs from the one-GPU image."""
     from PIL import Image
     path = os.path.join(SCENES, "CornellBox2.json")
     args = [path, "--res", "128", "128", "--ssaa", "2", "--sample", "16"]
