@@ -268,6 +268,12 @@ int mrt_spp_per_launch(mrt_ctx* ctx, uint32_t spp, uint32_t* current);
  * on-disk cache instead).  A compile error text is left in mrt_last_error. */
 int mrt_jit_status(mrt_ctx* ctx, uint32_t* eligible, uint32_t* compiled, uint64_t* launches, double* compile_seconds);
 
+/* How the library decided to render the scene it holds: through a scene-level BVH (scenes above ~60 box-equivalents;
+ * smaller ones are unrolled into the kernel), with the pooled kernel (lanes take (pixel, sample) items from their
+ * warp's pool instead of owning a pixel: scenes that search a BVH), and the feature mask of the kernel
+ * (1 lights, 2 textures, 4 transmission, 8 meshes). */
+int mrt_scene_info(mrt_ctx* ctx, uint32_t* scene_bvh, uint32_t* pooled, uint32_t* features);
+
 /* Counters of the kernels this context launched (bench.py's gpu_launches). */
 int mrt_launch_count(mrt_ctx* ctx, uint64_t* n);
 /* Measured FP32 FMA peak of the device this context lives on, in TFLOP/s

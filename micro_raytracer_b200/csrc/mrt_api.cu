@@ -91,7 +91,7 @@ int launch_samples(mrt_ctx* c, uint32_t sample0, uint32_t stride, uint32_t count
         fp.n_samples = n;
         cudaError_t e = use_jit ? (c->gscene.bvh ? mrt_jit_launch_bvh(c->jit_kernel, c->gscene, fp, c->stream)
                                                  : mrt_jit_launch(c->jit_kernel, c->gscene.c, fp, c->stream))
-                                : mrt_launch_path(c->features, c->in_param, c->pscene, &c->gscene, fp, c->stream);
+                                : mrt_launch_path(c->features, c->in_param, c->pool, c->pscene, &c->gscene, fp, c->stream);
         if (e != cudaSuccess) return cuda_fail(c, e, "path kernel launch");
         if (use_jit) c->jit_launches++;
         c->launches++;
@@ -725,6 +725,16 @@ int mrt_jit_status(mrt_ctx* c, uint32_t* eligible, uint32_t* compiled, uint64_t*
     if (launches) *launches = c->jit_launches;
     if (compile_seconds && !c->jit_from_disk) *compile_seconds = c->jit_seconds;
     if (!c->jit_err.empty()) c->err = c->jit_err;  // readable through mrt_last_error
+    return MRT_OK;
+}
+
+int mrt_scene_info(mrt_ctx* c, uint32_t* scene_bvh, uint32_t* pooled, uint32_t* features) {
+    if (!c) return MRT_ERR_INVALID;
+    if (!c->have_scene) return fail(c, MRT_ERR_STATE, "scene_info before set_scene");
+    const mrt_ctx* f = film_ctx(c);
+    if (scene_bvh) *scene_bvh = f->gscene.bvh ? 1u : 0u;
+    if (pooled) *pooled = f->pool ? 1u : 0u;
+    if (features) *features = f->features;
     return MRT_OK;
 }
 

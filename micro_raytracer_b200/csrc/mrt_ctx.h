@@ -135,6 +135,7 @@ struct mrt_ctx {
 
     // scene
     bool have_scene = false, in_param = false;
+    bool pool = false;             // the scene is rendered by the pooled kernel (lanes unbound from pixels)
     uint32_t features = 0;
     ParamScene* pscene = nullptr;  // host staging copies of the kernel-parameter structs
     GlobalScene gscene{};

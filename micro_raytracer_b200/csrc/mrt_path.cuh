@@ -26,31 +26,165 @@ __device__ __forceinline__ void camera_ray(const FilmParams& fp, f3 q, float u1,
     *d = dd;
 }
 
+#ifndef MRT_POOL_BLOCK
+#define MRT_POOL_BLOCK 128  // threads per block of the pooled kernels (= MRT_PATH_BLOCK)
+#endif
+struct PathState {
+    f3 o, d;          // current ray
+    f3 T;             // throughput of the path so far: prod (0.5 + color_i) pwr_i   (rt.rs:990-992, forward form)
+    float pwr;        // ray.pwr: (1 - loss)^bounce   (rt.rs:571)
+    uint32_t bounce;  // MRT_NEED_PATH: the lane needs a new camera path
+};
+#define MRT_NEED_PATH 0xffffffffu
+
+// One path segment: RaytraceIterator::next (rt.rs:1014-1066) and the step of RayTracer::reduce_light (rt.rs:956-994,
+// evaluated forward) that belongs to it.  Adds the segment's radiance to `acc` and advances `p` to the next ray;
+// returns true when the path ended here (miss, emission, bounce limit).
 template <class V, uint32_t F>
-__device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
-    // Pixel of this thread.  Tiled: a warp renders an 8x4 tile and a block 16x8, so the lanes of a warp look at
-    // neighbouring surfaces (paths of similar length, similar BVH traversals); the RNG and the accumulator are
-    // keyed by the PIXEL, so the image does not depend on the mapping.
-    uint32_t px, py;
+__device__ __forceinline__ bool path_segment(const V& sc, const FilmParams& fp, uint32_t pix, uint32_t sample, PathState& p, f3& acc) {
+    const SceneCommon& c = sc.c();
+    const f3 o = p.o, d = p.d;
+    HitRec h;
+    const bool hit = closest_hit<V, F, false, (F & F_TRANSMIT) != 0>(sc, o, d, &h);
+    if (!hit) {
+        // primary miss: sky.color (rt.rs:958); later miss: fold seed sky.color*sky.pwr (rt.rs:964)
+#if !(defined(MRT_JIT) && defined(MRT_JIT_SKY_BLACK))  // a black sky adds nothing: compiled out when the scene says so
+        if (p.bounce == 0) acc = acc + mk(c.sky[0], c.sky[1], c.sky[2]);
+        else acc = acc + p.T * mk(c.sky_tail[0], c.sky_tail[1], c.sky_tail[2]);
+#endif
+        return true;
+    }
+    const FatInst* fat = c.fat + h.inst;
+    Surf s;
+    load_surf(fat, &s);
+    f3 hp = fma3(d, h.t0, o);
+    f3 pl = to_local(s, hp);
+    f3 n = surf_normal<F>(c, s, pl, h.tri0);
+    Mat m;
+    load_mat<F>(c, fat, s, pl, &m);
+
+    // light visibility from the entry hit, rt.rs:1027-1045 (no distance limit)
+    uint32_t vis = 0;
+    if constexpr ((F & F_LIGHTS) != 0) {
+        for (uint32_t li = 0; li < MRT_N_LIGHTS(c); li++) {
+            const float4 lv = c.light[li].v_kind;
+            f3 l = (__float_as_uint(lv.w) == 0u) ? normalize(xyz(lv) - hp) : xyz(lv);
+            HitRec dummy;
+            if (!closest_hit<V, F, true, false>(sc, fma3(l, MRT_E, hp), l, &dummy)) vis |= 1u << li;
+        }
+    }
+
+    const uint4 uw = rng_words(pix, sample, 1u + 2u * p.bounce, fp.key);  // x: reflect lottery, y z: direction, w: emission draw
+
+    // Ray::reflect from the entry hit, rt.rs:559-572
+    f3 nd, no;
+    {
+        float rough = m.rough;
+        if (m.metal_raw == 0.0f && m.opacity != 0.0f && uw.x < MRT_LOTTERY_80) rough = 1.0f;  // u < 0.8
+        const f3 nn = rand_normal_w(n, rough, uw.y, uw.z);
+        nd = reflect3(d, nn);  // unit d about unit nn stays unit (the reference's .norm() is a no-op to 1e-7)
+        no = fma3(nd, MRT_E, hp);
+    }
+    // 15 % chance to keep reflecting for transparent material, rt.rs:1051-1059
+    if constexpr ((F & F_TRANSMIT) != 0) {
+        const float pt = fminf(1.0f - m.opacity, 0.85f);
+        if (pt > 0.0f) {
+            const float4 ub = rng_block(pix, sample, 2u + 2u * p.bounce, fp.key);
+            if (ub.x < pt) {
+                // exit hit: point, normal and material at t1 (rt.rs:886-894)
+                const f3 hp1 = fma3(d, h.t1, o);
+                const f3 pl1 = to_local(s, hp1);
+                const f3 n1 = surf_normal<F>(c, s, pl1, h.tri1);
+                Mat m1;
+                load_mat<F>(c, fat, s, pl1, &m1);
+                // Ray::refract, rt.rs:574-589 ; Vec3f::refract, lin.rs:96-105
+                float rough = m1.rough;
+                if (m1.metal_raw == 0.0f && m1.opacity != 0.0f && ub.y < 0.80f) rough = 1.0f;
+                const f3 nn = rand_normal(n1, rough, ub.z, ub.w);
+                const float eta = 1.0f + 0.5f * m1.glass;
+                const float cs = -dot(nn, d);
+                const float k = 1.0f - eta * eta * (1.0f - cs * cs);
+                if (k >= 0.0f) {
+                    const f3 rd = normalize(fma3(nn, cs * eta + sqrtf(k), d * eta));
+                    nd = rd;
+                    no = fma3(rd, MRT_E, hp1);
+                    hp = hp1; n = n1; m = m1;  // the recorded hit is the exit hit
+                }
+            }
+        }
+    }
+
+    // ---- RayTracer::reduce_light, rt.rs:956-994, evaluated forward
+#if defined(MRT_JIT) && defined(MRT_JIT_EMIT_BINARY)
+    // every emit of the scene is 0 or 1 (no emap): gen_bool(1) is always true, gen_bool(0) never — no draw needed
+    if (m.emit != 0.0f) {
+#else
+    if ((float)uw.w * MRT_U32_TO_UNIT < m.emit) {  // emission draw, rt.rs:966-970
+#endif
+        acc = acc + p.T * m.color;
+        return true;
+    }
+    if constexpr ((F & F_LIGHTS) != 0) {
+        f3 lc = mk(0.f, 0.f, 0.f);
+        for (uint32_t li = 0; li < MRT_N_LIGHTS(c); li++) {
+            if (!((vis >> li) & 1u)) continue;
+            const float4 lv = c.light[li].v_kind;
+            const float4 cp = c.light[li].color_pwr;
+            const f3 l = (__float_as_uint(lv.w) == 0u) ? normalize(xyz(lv) - hp) : xyz(lv);
+            const float diff = fmaxf(dot(l, n), 0.0f);
+            float sp = fmaxf(dot(d, reflect3(l, n)), 0.0f);
+            sp *= sp; sp *= sp; sp *= sp; sp *= sp; sp *= sp;  // powi(32), rt.rs:981
+            sp *= (1.0f - m.rough);
+            const f3 oc = m.color * ((1.0f - m.metal) * diff);
+            lc = lc + mk(fmaf(oc.x, cp.x, sp), fmaf(oc.y, cp.y, sp), fmaf(oc.z, cp.z, sp)) * cp.w;
+        }
+        acc = acc + p.T * (lc * p.pwr);
+    }
+    p.T = p.T * mk((0.5f + m.color.x) * p.pwr, (0.5f + m.color.y) * p.pwr, (0.5f + m.color.z) * p.pwr);  // rt.rs:990-992
+    p.o = no; p.d = nd;
+    p.pwr *= fp.keep;
+    p.bounce++;
+    // a NaN direction (|n + r v| = 0) would poison the lane: end the path as a miss
+    const bool bad = !(fabsf(nd.x) <= 2.0f);
+    if (p.bounce > fp.max_bounce || bad) {  // rt.rs:1018
+#if !(defined(MRT_JIT) && defined(MRT_JIT_SKY_BLACK))
+        acc = acc + p.T * mk(c.sky_tail[0], c.sky_tail[1], c.sky_tail[2]);
+#endif
+        return true;
+    }
+    return false;
+}
+
+// Pixel of this thread.  Tiled: a warp renders an 8x4 tile and a block 16x8, so the lanes of a warp look at
+// neighbouring surfaces (paths of similar length, similar BVH traversals); the RNG and the accumulator are
+// keyed by the PIXEL, so the image does not depend on the mapping.
+__device__ __forceinline__ void thread_pixel(const FilmParams& fp, uint32_t* px, uint32_t* py) {
     if (fp.tiles_x) {
         const uint32_t by = blockIdx.x / fp.tiles_x, bx = blockIdx.x - by * fp.tiles_x;
         const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-        px = bx * 16u + (w & 1u) * 8u + (lane & 7u);
-        py = by * 8u + (w >> 1) * 4u + (lane >> 3);
+        *px = bx * 16u + (w & 1u) * 8u + (lane & 7u);
+        *py = by * 8u + (w >> 1) * 4u + (lane >> 3);
     } else {
         const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-        py = i / fp.nw; px = i - py * fp.nw;
+        *py = i / fp.nw; *px = i - *py * fp.nw;
     }
+}
+
+// The megakernel body, one thread per supersampled pixel: the lane renders its pixel's samples back to back.
+template <class V, uint32_t F>
+__device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
+    uint32_t px, py;
+    thread_pixel(fp, &px, &py);
     if (px >= fp.nw || py >= fp.nh || fp.n_samples == 0u) return;
     const uint32_t pix = py * fp.nw + px;
-    const SceneCommon& c = sc.c();
     const f3 q = pixel_focus_vec(fp, px, py);
     const uint32_t cam_seed = cam_hash_seed(pix, fp.key);
 
     f3 acc = mk(0.f, 0.f, 0.f);
-    f3 o = mk(0.f, 0.f, 0.f), d = mk(0.f, 1.f, 0.f), T = mk(1.f, 1.f, 1.f);
-    float pwr = 1.0f;
-    uint32_t bounce = 0xffffffffu;  // "needs a new camera path"
+    PathState p;
+    p.o = mk(0.f, 0.f, 0.f); p.d = mk(0.f, 1.f, 0.f); p.T = mk(1.f, 1.f, 1.f);
+    p.pwr = 1.0f;
+    p.bounce = MRT_NEED_PATH;
     uint32_t j = 0;
 
     // One iteration = one path segment.  A lane whose path ended (miss, emission, bounce limit)
@@ -61,133 +195,88 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
     // bounce-limit exits into predicated straight-line code costs more issue slots than the
     // divergent blocks it removes.
     for (;;) {
-        if (bounce == 0xffffffffu) {
+        if (p.bounce == MRT_NEED_PATH) {
             if (j >= fp.n_samples) break;
             const float2 u = rng_cam(cam_seed, fp.sample0 + j * fp.sample_stride);
-            camera_ray(fp, q, u.x, u.y, &o, &d);
-            T = mk(1.f, 1.f, 1.f);
-            pwr = 1.0f;
-            bounce = 0;
+            camera_ray(fp, q, u.x, u.y, &p.o, &p.d);
+            p.T = mk(1.f, 1.f, 1.f);
+            p.pwr = 1.0f;
+            p.bounce = 0;
         }
         const uint32_t sample = fp.sample0 + j * fp.sample_stride;
-
-        // ---- RaytraceIterator::next, rt.rs:1014-1066
-        HitRec h;
-        const bool hit = closest_hit<V, F, false, (F & F_TRANSMIT) != 0>(sc, o, d, &h);
-        if (!hit) {
-            // primary miss: sky.color (rt.rs:958); later miss: fold seed sky.color*sky.pwr (rt.rs:964)
-#if !(defined(MRT_JIT) && defined(MRT_JIT_SKY_BLACK))  // a black sky adds nothing: compiled out when the scene says so
-            if (bounce == 0) acc = acc + mk(c.sky[0], c.sky[1], c.sky[2]);
-            else acc = acc + T * mk(c.sky_tail[0], c.sky_tail[1], c.sky_tail[2]);
-#endif
-            bounce = 0xffffffffu; j++;
-            continue;
-        }
-        {
-            const FatInst* fat = c.fat + h.inst;
-            Surf s;
-            load_surf(fat, &s);
-            f3 hp = fma3(d, h.t0, o);
-            f3 pl = to_local(s, hp);
-            f3 n = surf_normal<F>(c, s, pl, h.tri0);
-            Mat m;
-            load_mat<F>(c, fat, s, pl, &m);
-
-            // light visibility from the entry hit, rt.rs:1027-1045 (no distance limit)
-            uint32_t vis = 0;
-            if constexpr ((F & F_LIGHTS) != 0) {
-                for (uint32_t li = 0; li < MRT_N_LIGHTS(c); li++) {
-                    const float4 lv = c.light[li].v_kind;
-                    f3 l = (__float_as_uint(lv.w) == 0u) ? normalize(xyz(lv) - hp) : xyz(lv);
-                    HitRec dummy;
-                    if (!closest_hit<V, F, true, false>(sc, fma3(l, MRT_E, hp), l, &dummy)) vis |= 1u << li;
-                }
-            }
-
-            const uint4 uw = rng_words(pix, sample, 1u + 2u * bounce, fp.key);  // x: reflect lottery, y z: direction, w: emission draw
-
-            // Ray::reflect from the entry hit, rt.rs:559-572
-            f3 nd, no;
-            {
-                float rough = m.rough;
-                if (m.metal_raw == 0.0f && m.opacity != 0.0f && uw.x < MRT_LOTTERY_80) rough = 1.0f;  // u < 0.8
-                const f3 nn = rand_normal_w(n, rough, uw.y, uw.z);
-                nd = reflect3(d, nn);  // unit d about unit nn stays unit (the reference's .norm() is a no-op to 1e-7)
-                no = fma3(nd, MRT_E, hp);
-            }
-            // 15 % chance to keep reflecting for transparent material, rt.rs:1051-1059
-            if constexpr ((F & F_TRANSMIT) != 0) {
-                const float p = fminf(1.0f - m.opacity, 0.85f);
-                if (p > 0.0f) {
-                    const float4 ub = rng_block(pix, sample, 2u + 2u * bounce, fp.key);
-                    if (ub.x < p) {
-                        // exit hit: point, normal and material at t1 (rt.rs:886-894)
-                        const f3 hp1 = fma3(d, h.t1, o);
-                        const f3 pl1 = to_local(s, hp1);
-                        const f3 n1 = surf_normal<F>(c, s, pl1, h.tri1);
-                        Mat m1;
-                        load_mat<F>(c, fat, s, pl1, &m1);
-                        // Ray::refract, rt.rs:574-589 ; Vec3f::refract, lin.rs:96-105
-                        float rough = m1.rough;
-                        if (m1.metal_raw == 0.0f && m1.opacity != 0.0f && ub.y < 0.80f) rough = 1.0f;
-                        const f3 nn = rand_normal(n1, rough, ub.z, ub.w);
-                        const float eta = 1.0f + 0.5f * m1.glass;
-                        const float cs = -dot(nn, d);
-                        const float k = 1.0f - eta * eta * (1.0f - cs * cs);
-                        if (k >= 0.0f) {
-                            const f3 rd = normalize(fma3(nn, cs * eta + sqrtf(k), d * eta));
-                            nd = rd;
-                            no = fma3(rd, MRT_E, hp1);
-                            hp = hp1; n = n1; m = m1;  // the recorded hit is the exit hit
-                        }
-                    }
-                }
-            }
-
-            // ---- RayTracer::reduce_light, rt.rs:956-994, evaluated forward
-#if defined(MRT_JIT) && defined(MRT_JIT_EMIT_BINARY)
-            // every emit of the scene is 0 or 1 (no emap): gen_bool(1) is always true, gen_bool(0) never — no draw needed
-            if (m.emit != 0.0f) {
-#else
-            if ((float)uw.w * MRT_U32_TO_UNIT < m.emit) {  // emission draw, rt.rs:966-970
-#endif
-                acc = acc + T * m.color;
-                bounce = 0xffffffffu; j++;
-                continue;
-            }
-            {
-                if constexpr ((F & F_LIGHTS) != 0) {
-                    f3 lc = mk(0.f, 0.f, 0.f);
-                    for (uint32_t li = 0; li < MRT_N_LIGHTS(c); li++) {
-                        if (!((vis >> li) & 1u)) continue;
-                        const float4 lv = c.light[li].v_kind;
-                        const float4 cp = c.light[li].color_pwr;
-                        const f3 l = (__float_as_uint(lv.w) == 0u) ? normalize(xyz(lv) - hp) : xyz(lv);
-                        const float diff = fmaxf(dot(l, n), 0.0f);
-                        float sp = fmaxf(dot(d, reflect3(l, n)), 0.0f);
-                        sp *= sp; sp *= sp; sp *= sp; sp *= sp; sp *= sp;  // powi(32), rt.rs:981
-                        sp *= (1.0f - m.rough);
-                        const f3 oc = m.color * ((1.0f - m.metal) * diff);
-                        lc = lc + mk(fmaf(oc.x, cp.x, sp), fmaf(oc.y, cp.y, sp), fmaf(oc.z, cp.z, sp)) * cp.w;
-                    }
-                    acc = acc + T * (lc * pwr);
-                }
-                T = T * mk((0.5f + m.color.x) * pwr, (0.5f + m.color.y) * pwr, (0.5f + m.color.z) * pwr);  // rt.rs:990-992
-                o = no; d = nd;
-                pwr *= fp.keep;
-                bounce++;
-                // a NaN direction (|n + r v| = 0) would poison the lane: end the path as a miss
-                const bool bad = !(fabsf(d.x) <= 2.0f);
-                if (bounce > fp.max_bounce || bad) {  // rt.rs:1018
-#if !(defined(MRT_JIT) && defined(MRT_JIT_SKY_BLACK))
-                    acc = acc + T * mk(c.sky_tail[0], c.sky_tail[1], c.sky_tail[2]);
-#endif
-                    bounce = 0xffffffffu; j++;
-                }
-            }
-        }
+        if (path_segment<V, F>(sc, fp, pix, sample, p, acc)) { p.bounce = MRT_NEED_PATH; j++; }
     }
     float4 a = fp.accum[pix];
     a.x += acc.x; a.y += acc.y; a.z += acc.z;
     fp.accum[pix] = a;
+}
+
+// The same kernel with the lanes UNBOUND from the pixels: a warp owns the (pixel, sample) items of its tile — 32
+// pixels x n_samples — and a lane that finishes a path takes the next item from the warp's counter, whichever pixel
+// it belongs to.  In scenes searched through a BVH the cost of a path varies by orders of magnitude between the
+// pixels of a tile (sky next to a mesh silhouette): bound to its pixel a lane on a cheap pixel runs out of samples
+// and idles for the rest of the launch (ncu, round 1: 5.8 - 10.9 of 32 lanes active); unbound, every lane works until
+// the tile's pool is dry.  The RNG is keyed by (pixel, global sample), so the paths are the same paths; only the
+// order in which a pixel's samples are summed changes.  Per warp in shared memory: the pixels' focus vectors and lens
+// seeds, their radiance sums (float atomics: at most a handful of lanes finish in the same iteration), the counter.
+template <class V, uint32_t F>
+__device__ __forceinline__ void path_body_pool(const V sc, const FilmParams& fp) {
+    __shared__ float4 s_q[MRT_POOL_BLOCK];        // focus vector of the pixel (xyz) + its film index (w, bits)
+    __shared__ float s_acc[3][MRT_POOL_BLOCK];
+    __shared__ uint32_t s_next[MRT_POOL_BLOCK / 32];
+    uint32_t px, py;
+    thread_pixel(fp, &px, &py);
+    const bool inside = px < fp.nw && py < fp.nh;
+    const uint32_t lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u, w = threadIdx.x >> 5;
+    const uint32_t valid = __ballot_sync(0xffffffffu, inside);
+    if (valid == 0u || fp.n_samples == 0u) return;  // warp-uniform
+    const uint32_t pix = py * fp.nw + px;
+    {
+        const f3 q = inside ? pixel_focus_vec(fp, px, py) : mk(0.f, 1.f, 0.f);
+        s_q[threadIdx.x] = make_float4(q.x, q.y, q.z, __uint_as_float(pix));
+        s_acc[0][threadIdx.x] = 0.0f; s_acc[1][threadIdx.x] = 0.0f; s_acc[2][threadIdx.x] = 0.0f;
+        if (lane == 0u) s_next[w] = 0u;
+    }
+    __syncwarp();
+    const uint32_t nvalid = (uint32_t)__popc(valid);
+    const uint32_t total = nvalid * fp.n_samples;
+    uint32_t tl = 0, sample = 0, tpix = 0;  // the item this lane is working on: tile lane, global sample, film index
+    f3 acc = mk(0.f, 0.f, 0.f);
+    PathState p;
+    p.o = mk(0.f, 0.f, 0.f); p.d = mk(0.f, 1.f, 0.f); p.T = mk(1.f, 1.f, 1.f);
+    p.pwr = 1.0f;
+    p.bounce = MRT_NEED_PATH;
+    bool have = false;
+    for (;;) {
+        if (p.bounce == MRT_NEED_PATH) {
+            if (have) {  // hand the finished path's radiance to its pixel
+                atomicAdd(&s_acc[0][wbase + tl], acc.x);
+                atomicAdd(&s_acc[1][wbase + tl], acc.y);
+                atomicAdd(&s_acc[2][wbase + tl], acc.z);
+                have = false;
+            }
+            const uint32_t item = atomicAdd(&s_next[w], 1u);
+            if (item >= total) break;
+            // items run sample-major: all pixels of the tile for one sample, then the next sample
+            const uint32_t jj = item / nvalid, k = item - jj * nvalid;
+            tl = valid == 0xffffffffu ? k : (uint32_t)__fns(valid, 0u, (int)k + 1);
+            sample = fp.sample0 + jj * fp.sample_stride;
+            const float4 qs = s_q[wbase + tl];
+            tpix = __float_as_uint(qs.w);
+            const float2 u = rng_cam(cam_hash_seed(tpix, fp.key), sample);
+            camera_ray(fp, xyz(qs), u.x, u.y, &p.o, &p.d);
+            p.T = mk(1.f, 1.f, 1.f);
+            p.pwr = 1.0f;
+            p.bounce = 0;
+            acc = mk(0.f, 0.f, 0.f);
+            have = true;
+        }
+        if (path_segment<V, F>(sc, fp, tpix, sample, p, acc)) p.bounce = MRT_NEED_PATH;
+    }
+    __syncwarp();
+    if (inside) {
+        float4 a = fp.accum[pix];
+        a.x += s_acc[0][threadIdx.x]; a.y += s_acc[1][threadIdx.x]; a.z += s_acc[2][threadIdx.x];
+        fp.accum[pix] = a;
+    }
 }

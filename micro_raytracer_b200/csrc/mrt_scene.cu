@@ -483,6 +483,10 @@ int mrt_scene_upload(mrt_ctx* c, const mrt_scene* s) {
     const size_t brute_cost = (6 * by_kind[K_BOX].size() + 14 * by_kind[K_SPHERE].size() + 15 * bxf.size() + 36 * by_kind[K_MESH].size()) / 6;
     bool use_bvh = brute_cost > bvh_min && prim_boxes.size() > 1 && prim_boxes_ok && prim_boxes.size() < (1u << 28) && !c->knobs.no_bvh;
     if (use_bvh) use_bvh = bvh_build_bounded(prim_boxes, &bvh_nodes, c->knobs.bvh_sah, &bvh_root);
+    // Lanes unbound from pixels (mrt_path.cuh: path_body_pool) wherever a BVH is searched — the scene's, or a mesh's:
+    // there the cost of a path varies wildly inside a warp's tile.  MRT_POOL=0 / 1 forces it off / on (A/B knob).
+    const bool use_pool = c->knobs.pool >= 0 ? c->knobs.pool != 0 : (use_bvh || (feat & F_MESH) != 0);
+    c->pool = use_pool;
     CK(c->d_bvh.upload(bvh_nodes));
     CK(c->d_mesh_m.upload(mesh_m));
     CK(c->d_fat.upload(fat));
@@ -611,6 +615,7 @@ int mrt_scene_upload(mrt_ctx* c, const mrt_scene* s) {
             if (binary) h += "#define MRT_JIT_EMIT_BINARY 1\n";
         }
         if (s->sky_color[0] == 0.0f && s->sky_color[1] == 0.0f && s->sky_color[2] == 0.0f) h += "#define MRT_JIT_SKY_BLACK 1\n";
+        if (use_pool) h += "#define MRT_JIT_POOL 1\n";
         h += "#define MRT_JIT_ROT " + std::to_string(rot_class) + "\n";
         h += "#define MRT_JIT_N_BOX " + std::to_string(cnt[K_BOX] + cnt[K_BOX_XF]) + "\n";
         h += "#define MRT_JIT_N_SPHERE " + std::to_string(cnt[K_SPHERE]) + "\n";

@@ -72,6 +72,7 @@ def declare(lib, prefix: str = "mrt_"):
         fn("update_scene", P, C.POINTER(abi.MrtScene))
         fn("update_frame", P, C.POINTER(abi.MrtFrame))
         fn("device_seconds", P, C.POINTER(C.c_double))
+        fn("scene_info", P, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32))
         fn("execute_async", P, u32)
         fn("sync", P)
         fn("accum_device", P, C.POINTER(P), C.POINTER(C.c_size_t), C.POINTER(P))
@@ -309,6 +310,12 @@ class Sampler:
         t = C.c_double()
         self._check(self._lib.mrt_device_seconds(self._ctx, C.byref(t)))
         return t.value
+
+    def kernel_info(self) -> dict:
+        """How the scene is rendered: scene-level BVH or unrolled, pooled kernel or one lane per pixel, feature mask."""
+        b, p, f = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._check(self._lib.mrt_scene_info(self._ctx, C.byref(b), C.byref(p), C.byref(f)))
+        return {"scene_bvh": bool(b.value), "pooled": bool(p.value), "features": f.value}
 
     def group_info(self) -> dict:
         n, p = C.c_uint32(), C.c_uint32()

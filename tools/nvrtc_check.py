@@ -18,21 +18,25 @@ DEFAULT = """
 #define MRT_JIT_FIRST_MESH 5
 #define MRT_JIT_F %du
 """
-MAIN = b'''#include "mrt_jit_scene.h"
-#include "mrt_path.cuh"
-extern "C" __global__ void __launch_bounds__(128) path_kernel_jit(const __grid_constant__ SceneCommon scene, const __grid_constant__ FilmParams fp) {
-    path_body<JitView, MRT_JIT_F>(JitView{scene}, fp);
-}
-'''
+def _main_src():
+    """k_main_src of csrc/mrt_jit.cu (the translation unit NVRTC compiles), read from the source so the two cannot drift."""
+    import re
+    t = open(os.path.join(src, "mrt_jit.cu")).read()
+    body = t[t.index("const char* k_main_src ="):]
+    body = body[:body.index(";\n")]
+    return "".join(bytes(m, "utf-8").decode("unicode_escape") for m in re.findall(r'"((?:[^"\\]|\\.)*)"', body)).encode()
 
-def compile_header(header: bytes, out=None):
+
+MAIN = _main_src()
+
+def compile_header(header: bytes, out=None, extra=()):
     n = C.CDLL("libnvrtc.so.12")
     prog = C.c_void_p()
     hs = [header, open(os.path.join(src, "mrt_path.cuh"), "rb").read(), open(os.path.join(src, "mrt_device.cuh"), "rb").read()]
     names = [b"mrt_jit_scene.h", b"mrt_path.cuh", b"mrt_device.cuh"]
     arr = (C.c_char_p * 3)(*hs); narr = (C.c_char_p * 3)(*names)
     assert n.nvrtcCreateProgram(C.byref(prog), MAIN, b"mrt_jit_main.cu", 3, arr, narr) == 0
-    opts = [b"--gpu-architecture=sm_100a", b"-std=c++17", b"-ftz=true", b"-prec-div=false", b"-prec-sqrt=false", b"-lineinfo", b"-DMRT_JIT=1"]
+    opts = [b"--gpu-architecture=sm_100a", b"-std=c++17", b"-ftz=true", b"-prec-div=false", b"-prec-sqrt=false", b"-lineinfo", b"-DMRT_JIT=1", *[e.encode() for e in extra]]
     rc = n.nvrtcCompileProgram(prog, len(opts), (C.c_char_p * len(opts))(*opts))
     ls = C.c_size_t(); n.nvrtcGetProgramLogSize(prog, C.byref(ls))
     log = C.create_string_buffer(ls.value or 1); n.nvrtcGetProgramLog(prog, log)
@@ -47,7 +51,7 @@ def compile_header(header: bytes, out=None):
 if __name__ == "__main__":
     import time
     if len(sys.argv) > 1 and os.path.exists(sys.argv[1]):
-        t = time.time(); size, log = compile_header(open(sys.argv[1], "rb").read(), sys.argv[2] if len(sys.argv) > 2 else None)
+        t = time.time(); size, log = compile_header(open(sys.argv[1], "rb").read(), sys.argv[2] if len(sys.argv) > 2 else None, sys.argv[3:])
         print("ok", size, "bytes", round(time.time() - t, 2), "s", log[:500])
     else:
         for f in (0, 15):
