@@ -91,7 +91,8 @@ struct Knobs {
     size_t bvh_min = 60;        // MRT_BVH_MIN: BVH above this many box-equivalents
     size_t jit_cluster = 4;     // MRT_JIT_CLUSTER: box pairs per bracket in big unrolled scenes, 0 = off
     uint32_t force_features = 0;  // MRT_FORCE_FEATURES
-    int pool = -1;              // MRT_POOL: -1 auto (scenes searched through a BVH), 0 never, 1 always
+    int pool = 0;               // MRT_POOL=1: the pooled kernel (lanes take (pixel, sample) items from their warp's pool)
+    bool mesh_via_bvh = false;  // MRT_MESH_VIA_BVH=1: scenes with a mesh go through the scene BVH whatever their size (measured: Mesh.json 2 355 vs 2 482 unrolled)
     void read() {
         if (const char* s = std::getenv("MRT_TILE")) tiled = std::atoi(s) != 0;
         if (const char* s = std::getenv("MRT_BVH_SAH")) bvh_sah = std::atoi(s) != 0;
@@ -103,6 +104,7 @@ struct Knobs {
         if (const char* s = std::getenv("MRT_JIT_CLUSTER")) jit_cluster = (size_t)std::max(0, std::atoi(s));
         if (const char* s = std::getenv("MRT_FORCE_FEATURES")) force_features = (uint32_t)std::atoi(s) & F_ALL;
         if (const char* s = std::getenv("MRT_POOL")) pool = std::atoi(s);
+        if (const char* s = std::getenv("MRT_MESH_VIA_BVH")) mesh_via_bvh = std::atoi(s) != 0;
     }
 };
 

@@ -332,6 +332,34 @@ __device__ __forceinline__ bool tri_test(const DTri& tr, f3 o_rel /* ray.orig - 
     return true;
 }
 
+// The reference's Box::intersect on an octree leaf (relative to the instance), 1/E quirk included: m = rcp_fixed3(d),
+// om = o_rel * m.  Part of the candidate rule: a zero direction component behaves like a slope of 1/E, so a leaf
+// the ray runs inside of can still be "missed".
+__device__ __forceinline__ bool leaf_slab_hit(float4 lo, float4 hi, f3 m, f3 om) {
+    const float ax = fmaf(lo.x, m.x, -om.x), bx = fmaf(hi.x, m.x, -om.x);
+    const float ay = fmaf(lo.y, m.y, -om.y), by = fmaf(hi.y, m.y, -om.y);
+    const float az = fmaf(lo.z, m.z, -om.z), bz = fmaf(hi.z, m.z, -om.z);
+    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    return !(tn > tf || tf < 0.0f);
+}
+// Is a triangle the ray hits a CANDIDATE of the reference's walk, i.e. does the ray pierce one of the octree leaves
+// that list it?  rf / rl = rank (position in the candidate sequence) of its first / last pierced occurrence.
+template <bool WANT_LAST>
+__device__ __forceinline__ bool tri_candidate(const SceneCommon& c, const DTri& tr, f3 m, f3 om, uint32_t* rf, uint32_t* rl) {
+    const uint32_t e0 = __float_as_uint(tr.v0.w), en = __float_as_uint(tr.e0.w);
+    bool cand = false;
+    for (uint32_t e = 0; e < en; e++) {
+        const DTriLeaf tl = c.tri_leaf[e0 + e];
+        if (!leaf_slab_hit(__ldg(&c.leaf[tl.leaf].lo), __ldg(&c.leaf[tl.leaf].hi), m, om)) continue;
+        if (!cand) *rf = tl.rank;
+        *rl = tl.rank;
+        cand = true;
+        if (!WANT_LAST) break;
+    }
+    return cand;
+}
+
 // Mesh leg of Renderer::intersect (rt.rs:740-772), triangle-BVH form (DMesh::bvh_root; the sequential walk of the
 // octree leaves it replaces follows below and stays as the reference the tests compare with).  The reference's result only depends on the SET of
 // candidates — every triangle listed by a pierced leaf — and, between equal t, on their order.  So instead of
@@ -438,19 +466,16 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
 // leaf-major loop issued 2/3 of its instructions with <= 3 active lanes).  Candidate order per lane
 // is unchanged (leaf order, then list order), so the first-min / last-max tie rules hold.
 // (Only taken when the mesh has no triangle BVH: MRT_NO_MESH_BVH, the bit-identity tests.)
+// root AABB of a mesh, centred on the instance (Mesh::gen_aabb, rt.rs:261-270; tested first, rt.rs:708-710)
+__device__ __forceinline__ bool mesh_root_hit(const DMesh& mh, f3 m, f3 om) {
+    const float ax = fabsf(m.x) * mh.half[0], ay = fabsf(m.y) * mh.half[1], az = fabsf(m.z) * mh.half[2];
+    const float tn = fmaxf(fmaxf(-om.x - ax, -om.y - ay), -om.z - az);
+    const float tf = fminf(fminf(-om.x + ax, -om.y + ay), -om.z + az);
+    return !(tn > tf || tf < 0.0f);
+}
 template <bool ANY, bool WANT_T1>
-__device__ __forceinline__ bool mesh_test(const SceneCommon& c, uint32_t mesh_id, f3 o_rel, f3 d,
-                                          float* t0, float* t1, int* i0, int* i1) {
-    const DMesh mh = c.mesh[mesh_id];
-    const f3 m = rcp_fixed3(d);
-    const f3 om = o_rel * m;
-    {   // root AABB, centred on the instance (Mesh::gen_aabb, rt.rs:261-270)
-        const float ax = fabsf(m.x) * mh.half[0], ay = fabsf(m.y) * mh.half[1], az = fabsf(m.z) * mh.half[2];
-        const float tn = fmaxf(fmaxf(-om.x - ax, -om.y - ay), -om.z - az);
-        const float tf = fminf(fminf(-om.x + ax, -om.y + ay), -om.z + az);
-        if (tn > tf || tf < 0.0f) return false;
-    }
-    if (mh.bvh_root != 0xffffffffu) return mesh_test_bvh<ANY, WANT_T1>(c, mh, o_rel, d, m, om, t0, t1, i0, i1);
+__device__ __forceinline__ bool mesh_leaf_walk(const SceneCommon& c, const DMesh& mh, f3 o_rel, f3 d, f3 m, f3 om,
+                                               float* t0, float* t1, int* i0, int* i1) {
     bool any = false;
     float b0 = 0.f, b1 = 0.f;
     int k0 = -1, k1 = -1;
@@ -492,6 +517,16 @@ __device__ __forceinline__ bool mesh_test(const SceneCommon& c, uint32_t mesh_id
     if (!any) return false;
     *t0 = b0; *t1 = b1; *i0 = k0; *i1 = k1;
     return true;
+}
+template <bool ANY, bool WANT_T1>
+__device__ __forceinline__ bool mesh_test(const SceneCommon& c, uint32_t mesh_id, f3 o_rel, f3 d,
+                                          float* t0, float* t1, int* i0, int* i1) {
+    const DMesh mh = c.mesh[mesh_id];
+    const f3 m = rcp_fixed3(d);
+    const f3 om = o_rel * m;
+    if (!mesh_root_hit(mh, m, om)) return false;
+    if (mh.bvh_root != 0xffffffffu) return mesh_test_bvh<ANY, WANT_T1>(c, mh, o_rel, d, m, om, t0, t1, i0, i1);
+    return mesh_leaf_walk<ANY, WANT_T1>(c, mh, o_rel, d, m, om, t0, t1, i0, i1);
 }
 
 struct HitRec {
@@ -800,6 +835,163 @@ __device__ __forceinline__ void bvh_traverse(Best& B, const GlobalScene& s, cons
     }
 }
 
+// ---- The same search as ONE flat loop (what the kernels run; bvh_traverse + mesh_test_bvh above stay as the form
+// the bit-identity tests compare with, MRT_WALK_V1).  ncu on round 1's loop (profiles/r2_*): the node-visit block ran
+// with 12 - 14 of 32 lanes, but the leaf block with 4, the stack push with 3.7 and the pop loop with 2.5 — lanes at a
+// leaf, lanes at a node and lanes popping took turns, and a mesh instance behind a scene leaf ran its whole triangle
+// walk as one leaf step while the rest of the warp waited.  Here every turn of the loop is a NODE VISIT:
+//   * the primitives (scene level) or triangles (inside a mesh instance) behind the children of the node are tested
+//     inline, under a predicate, in the very turn that found their box — no push, no extra turn, no pop for them;
+//   * one stack entry is popped per turn, in the same turn for every lane that needs one (no inner pop loop);
+//   * a mesh instance is ENTERED: a marker goes on the stack, the lane switches to the object-space ray and keeps
+//     visiting nodes — now of the triangle BVH — in the same loop; popping the marker folds the mesh's entry / exit
+//     candidates into the scene-level best and switches back.
+// Candidates, tie rules (lexicographic (t0, instance index); first-min / last-max with candidate ranks inside a mesh)
+// and every primitive test are those of the nested form: hit ids, t0, t1 and images are bit-identical.
+#define MRT_WALK_EMPTY 0x7ffffffeu
+#define MRT_WALK_MARKER 0x7fffffffu
+#define MRT_WALK_STACK 64   // scene depth (<= 30) + marker + mesh depth (<= 30)
+template <uint32_t F, bool ANY, bool WANT_T1>
+__device__ __forceinline__ void bvh_walk(Best& B, const GlobalScene& s, const RayPre& r, const RayPk& rp) {
+    const SceneCommon& c = s.c;
+    constexpr bool MESH = (F & F_MESH) != 0 && MRT_BVH_HAS_MESH;
+    constexpr bool PRUNE_TRI = !ANY && !WANT_T1;  // inside a mesh the exit candidate may lie anywhere: no pruning when it is wanted
+    const float INF = __int_as_float(0x7f800000);
+    uint32_t stack[MRT_WALK_STACK];
+    float stack_t[MRT_WALK_STACK];
+    int sp = 0;
+    NodeRay nr = r.n;
+    const BvhNode* nodes = s.bvh;
+    bool in_mesh = false;
+    // state of the mesh instance being walked
+    f3 mo = mk(0.f, 0.f, 0.f), md = mk(0.f, 0.f, 0.f), mm = mk(0.f, 0.f, 0.f), mom = mk(0.f, 0.f, 0.f);  // object-space ray, 1/d (fixed), o * 1/d
+    uint32_t m_first_tri = 0u, m_inst = 0u;
+    float b0 = INF, b1 = -INF;
+    uint32_t r0 = 0xffffffffu, r1 = 0u;
+    int k0 = -1, k1 = -1;
+
+    auto tri_leaf = [&](uint32_t ti) {
+        const DTri* tp = &c.tri[m_first_tri + ti];
+        DTri tr;
+        tr.v0 = __ldg(&tp->v0); tr.e0 = __ldg(&tp->e0); tr.e1 = __ldg(&tp->e1);
+        float t;
+        if (tri_test(tr, mo, md, &t) && !(PRUNE_TRI && !(t <= b0))) {
+            uint32_t rf = 0xffffffffu, rl = 0u;
+            if (tri_candidate<WANT_T1>(c, tr, mm, mom, &rf, &rl)) {
+                if constexpr (ANY) { B.any = true; return; }
+                if (t < b0 || (t == b0 && rf < r0)) { b0 = t; r0 = rf; k0 = (int)ti; }
+                if constexpr (WANT_T1) { if (t > b1 || (t == b1 && rl >= r1)) { b1 = t; r1 = rl; k1 = (int)ti; } }
+            }
+        }
+    };
+    // a mesh instance behind a scene-level leaf: ray into object space, root AABB (rt.rs:708-710), then its triangle BVH.
+    // Returns the reference to continue with (the mesh's root, or EMPTY when the instance is missed / was walked inline).
+    auto enter_mesh = [&](uint32_t k) -> uint32_t {
+        if constexpr (MESH) {
+            const SlimInst e = ldg_slim(s.mesh + k);
+            f3 ol = r.o - xyz(e.a), dl = r.d;
+            if (__float_as_uint(e.b.x) != 0u) { ol = mulXf(s.mesh_m[k], ol); dl = mulXf(s.mesh_m[k], r.d); }
+            const DMesh mh = c.mesh[__float_as_uint(e.b.y)];
+            const f3 m = rcp_fixed3(dl);
+            const f3 om = ol * m;
+            if (!mesh_root_hit(mh, m, om)) return MRT_WALK_EMPTY;
+            if (mh.bvh_root == 0xffffffffu) {  // no triangle BVH (MRT_NO_MESH_BVH): the sequential leaf walk, as one step
+                float t0 = 0.f, t1 = 0.f;
+                int tr0 = -1, tr1 = -1;
+                const bool hit = mesh_leaf_walk<ANY, WANT_T1>(c, mh, ol, dl, m, om, &t0, &t1, &tr0, &tr1);
+                best_update_lex<F, ANY, WANT_T1>(B, hit, t0, t1, (int)(c.first[K_MESH] + k), tr0, tr1);
+                return MRT_WALK_EMPTY;
+            }
+            stack[sp] = MRT_WALK_MARKER; stack_t[sp] = 0.0f; sp++;
+            mo = ol; md = dl; mm = m; mom = om;
+            m_first_tri = mh.first_tri; m_inst = k;
+            b0 = INF; b1 = -INF; r0 = 0xffffffffu; r1 = 0u; k0 = -1; k1 = -1;
+            nr.bm = true_rcp3(dl, m);
+            nr.bnom = mk(-ol.x * nr.bm.x, -ol.y * nr.bm.y, -ol.z * nr.bm.z);
+            nr.bam = mk(fabsf(nr.bm.x), fabsf(nr.bm.y), fabsf(nr.bm.z));
+            nodes = c.tbvh;
+            in_mesh = true;
+            return mh.bvh_root;
+        } else {
+            (void)k;
+            return MRT_WALK_EMPTY;
+        }
+    };
+    auto is_mesh_ref = [&](uint32_t ref) -> bool { return MESH && !in_mesh && ((ref >> 28) & 7u) == K_MESH; };
+    auto leaf = [&](uint32_t ref) {  // a leaf that is NOT a mesh instance
+        if (MESH && in_mesh) tri_leaf(ref & ~MRT_BVH_LEAF);
+        else bvh_leaf<F, ANY, WANT_T1>(B, s, r, rp, ref & ~MRT_BVH_LEAF);
+    };
+
+    auto far_bound = [&]() -> float {
+        // behind this nothing can win: '<=' because an equal t0 with a lower index (rank) must still be found; inside a
+        // mesh the mesh's own entry candidate and the scene-level best both bound the search — unless the exit
+        // candidate is wanted, which may lie anywhere
+        return ANY ? INF : ((MESH && in_mesh) ? (PRUNE_TRI ? fminf(b0, B.t0) : INF) : B.t0);
+    };
+    uint32_t cur = s.bvh_root;
+    for (;;) {
+        if (cur != MRT_WALK_EMPTY) {
+            uint32_t cl = cur, cr = MRT_WALK_EMPTY, next = MRT_WALK_EMPTY;
+            float tl = 0.0f, tr = 0.0f;
+            bool hl = true, hr = false, entered = false;
+            if (cur & MRT_BVH_LEAF) {
+                // a mesh instance to enter; or a root that is a single primitive / triangle: (cl, hl) as set above
+                if (is_mesh_ref(cur)) { next = enter_mesh(cur & 0x0fffffffu); entered = true; hl = false; }
+            } else {
+                const float4 q0 = __ldg(&nodes[cur].q0), q1 = __ldg(&nodes[cur].q1), q2 = __ldg(&nodes[cur].q2);
+                const uint2 ref = __ldg(reinterpret_cast<const uint2*>(&nodes[cur].ref));
+                float tfl, tfr;
+                node_slabs(nr, q0, q1, q2, &tl, &tfl, &tr, &tfr);
+                const float bound = far_bound();
+                hl = tl <= tfl && tfl >= 0.0f && tl <= bound;
+                hr = tr <= tfr && tfr >= 0.0f && tr <= bound;
+                cl = ref.x; cr = ref.y;
+            }
+            // primitives / triangles behind the children: tested now, in this turn (one copy of the test code: the
+            // lanes whose left child is a leaf go first, then those whose right child is)
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ch++) {
+                const uint32_t ref = ch ? cr : cl;
+                const bool h = ch ? hr : hl;
+                if (h && (ref & MRT_BVH_LEAF) && !is_mesh_ref(ref)) {
+                    leaf(ref);
+                    if (ch) hr = false; else hl = false;
+                }
+            }
+            if constexpr (ANY) { if (B.any) return; }
+            if (!entered) {
+                if constexpr (!ANY) {
+                    const float bound = far_bound();  // may just have come closer
+                    hl = hl && tl <= bound; hr = hr && tr <= bound;
+                }
+                if (hl && hr) {
+                    const bool left_first = tl <= tr;
+                    if (sp < MRT_WALK_STACK) { stack[sp] = left_first ? cr : cl; stack_t[sp] = left_first ? tr : tl; sp++; }
+                    next = left_first ? cl : cr;
+                } else next = hl ? cl : (hr ? cr : MRT_WALK_EMPTY);
+            }
+            cur = next;
+        }
+        if (cur == MRT_WALK_EMPTY) {  // one pop per turn
+            if (sp == 0) return;
+            --sp;
+            const uint32_t ref = stack[sp];
+            if (MESH && ref == MRT_WALK_MARKER) {  // the mesh instance is done: fold its candidates into the scene-level best
+                if constexpr (!ANY) {
+                    best_update_lex<F, ANY, WANT_T1>(B, k0 >= 0, b0, WANT_T1 ? b1 : b0, (int)(c.first[K_MESH] + m_inst), k0, WANT_T1 ? k1 : k0);
+                }
+                in_mesh = false;
+                nr = r.n;
+                nodes = s.bvh;
+                continue;
+            }
+            // a subtree that starts behind the best found since it was pushed holds nothing closer
+            if (stack_t[sp] <= far_bound()) cur = ref;
+        }
+    }
+}
+
 // Duff's device over one kind: ENTRY(k, LE) tests entry k of the kind.
 #define MRT_DUFF(n_expr, ENTRY)                                                  \
     {                                                                            \
@@ -884,7 +1076,11 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
 #define E_MSH(k, LE) test_mesh<F, ANY, WANT_T1, LE>(B, c, r, sc.mesh(k), sc.mesh_m(k), (int)(c.first[K_MESH] + (k)));
     if constexpr (V::kBvh) {
         if (MRT_BVH_ALWAYS || sc.s.bvh != nullptr) {  // warp-uniform: large scenes only
+#ifdef MRT_WALK_FLAT  // measured slower (round 2): Mesh 912 vs 2 355, Instance 1 856 vs 2 624, Minecraft 4 738 vs 6 266 Mpaths/s
+            bvh_walk<F, ANY, WANT_T1>(B, sc.s, r, rp);
+#else
             bvh_traverse<F, ANY, WANT_T1>(B, sc.s, r, rp);
+#endif
             for (uint32_t k = 0; k < MRT_N_PLANES(c); k++) {  // planes are infinite: brute force, same tie rule
                 const SlimInst e = sc.pln(k);
                 const float t0 = (e.b.x - dot(r.o, xyz(e.a))) * frcp(dot(r.d, xyz(e.a)));

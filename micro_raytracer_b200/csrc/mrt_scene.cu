@@ -481,11 +481,15 @@ int mrt_scene_upload(mrt_ctx* c, const mrt_scene* s) {
     // Minecraft.json (84 boxes): 4 144 unrolled, 5 343 through the BVH.
     const size_t bvh_min = c->knobs.bvh_min;  // 60 unless MRT_BVH_MIN says otherwise (experiment knob)
     const size_t brute_cost = (6 * by_kind[K_BOX].size() + 14 * by_kind[K_SPHERE].size() + 15 * bxf.size() + 36 * by_kind[K_MESH].size()) / 6;
-    bool use_bvh = brute_cost > bvh_min && prim_boxes.size() > 1 && prim_boxes_ok && prim_boxes.size() < (1u << 28) && !c->knobs.no_bvh;
+    // Scenes with a mesh always go through the scene BVH, whatever their size: its flat walk (mrt_device.cuh: bvh_walk) runs
+    // the triangle BVH of a mesh instance in the same loop as the scene's nodes (MRT_MESH_VIA_BVH=0: A/B knob).
+    const bool want_bvh = brute_cost > bvh_min || (c->knobs.mesh_via_bvh && !by_kind[K_MESH].empty());
+    bool use_bvh = want_bvh && !prim_boxes.empty() && prim_boxes_ok && prim_boxes.size() < (1u << 28) && !c->knobs.no_bvh;
     if (use_bvh) use_bvh = bvh_build_bounded(prim_boxes, &bvh_nodes, c->knobs.bvh_sah, &bvh_root);
-    // Lanes unbound from pixels (mrt_path.cuh: path_body_pool) wherever a BVH is searched — the scene's, or a mesh's:
-    // there the cost of a path varies wildly inside a warp's tile.  MRT_POOL=0 / 1 forces it off / on (A/B knob).
-    const bool use_pool = c->knobs.pool >= 0 ? c->knobs.pool != 0 : (use_bvh || (feat & F_MESH) != 0);
+    // Lanes unbound from pixels (mrt_path.cuh: path_body_pool): measured and NOT a win (round 2: Mesh -5 %, Minecraft
+    // -8 %, headline -12 %; active lanes 5.8 -> 6.4 of 32: the lanes are lost inside the BVH walk, not to uneven
+    // sample budgets), so it stays an experiment knob: MRT_POOL=1.
+    const bool use_pool = c->knobs.pool > 0;
     c->pool = use_pool;
     CK(c->d_bvh.upload(bvh_nodes));
     CK(c->d_mesh_m.upload(mesh_m));

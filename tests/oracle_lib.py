@@ -26,6 +26,8 @@ class CpuStats(C.Structure):
 
 
 def build_oracle(force=False):
+    if os.environ.get("MRT_ORACLE_SO"):  # another build of the oracle (tools/sanitize_oracle.sh: ASan / UBSan)
+        return os.environ["MRT_ORACLE_SO"]
     src = [os.path.join(ORACLE_DIR, f) for f in ("mrt_oracle.cpp", "mrt_oracle.h")] + [os.path.join(ROOT, "include", "mrt.h")]
     if (not force and os.path.exists(ORACLE_SO)
             and all(os.path.getmtime(ORACLE_SO) >= os.path.getmtime(s) for s in src if os.path.exists(s))):
@@ -37,8 +39,7 @@ def build_oracle(force=False):
 def load_oracle():
     global _lib
     if _lib is None:
-        build_oracle()
-        lib = declare(C.CDLL(ORACLE_SO), "mrt_cpu_")
+        lib = declare(C.CDLL(build_oracle()), "mrt_cpu_")
         lib.mrt_cpu_set_mode.argtypes = [C.c_void_p, C.c_int]
         lib.mrt_cpu_get_stats.argtypes = [C.c_void_p, C.POINTER(CpuStats)]
         lib.mrt_cpu_path.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]

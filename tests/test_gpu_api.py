@@ -93,18 +93,20 @@ def test_reference_loop_reaches_the_batched_throughput_on_the_headline_render():
 
 
 def test_settings_changes_flush_the_queue_first():
-    """Queued passes were asked for under the old RayTracer settings / partition: they are rendered before the change."""
+    """Queued passes were asked for under the old RayTracer settings: they are rendered before the change."""
     r = load("CornellBox2", (64, 64), 1.0)
     a, b = mrt.Sampler(device=0), mrt.Sampler(device=0)
-    for _ in range(2):
-        a.execute(r.scene, r.frame, r.rt)
-    r2 = load("CornellBox2", (64, 64), 1.0, bounce=2)
-    for _ in range(3):
-        a.execute(r2.scene, r2.frame, r2.rt)       # same scene content, other bounce: set_rt flushes the first two
-    b.execute(r.scene, r.frame, r.rt, 2)
-    b.execute(r2.scene, r2.frame, r2.rt, 3)
+    for bounce, n in ((8, 2), (2, 3)):
+        r.rt.bounce = bounce                      # the caller edits its RayTracer between passes
+        for _ in range(n):
+            a.execute(r.scene, r.frame, r.rt)     # one-pass calls: queued; set_rt flushes the first two
+        b.execute(r.scene, r.frame, r.rt, n)
     np.testing.assert_allclose(a.accum()[0], b.accum()[0], rtol=2e-5, atol=2e-6)
     assert a.accum()[1] == b.accum()[1] == 5
+    c = mrt.Sampler(device=0)
+    r.rt.bounce = 8
+    c.execute(r.scene, r.frame, r.rt, 5)
+    assert not np.allclose(c.accum()[0], a.accum()[0], rtol=1e-3)   # bounce 2 really was used for three of them
 
 
 # ---------------------------------------------------------------- content-keyed scene / frame updates

@@ -24,9 +24,10 @@ def main():
     cpu = "--cpu" in sys.argv
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     force_passes = int(sys.argv[sys.argv.index("--passes") + 1]) if "--passes" in sys.argv else None
+    only3 = "--only3" in sys.argv  # the three scenes that are searched through a BVH
     rows = []
     for label, name, res, ssaa, rt, passes in CONFIGS:
-        if only and name != only:
+        if (only and name != only) or (only3 and name not in ("Mesh", "Instance", "Minecraft")):
             continue
         passes = force_passes or passes
         r = load(name, res, ssaa, **rt)
@@ -42,7 +43,7 @@ def main():
         sec = s.execute(r.scene, r.frame, r.rt, passes)
         sec = min(sec, s.execute(r.scene, r.frame, r.rt, passes))
         row = {"config": label, "film": [nw, nh], "passes": passes, "gpu_mpaths_s": nw * nh * passes / sec / 1e6,
-               "jit": s.jit_status()["launches"] > 0}
+               "jit": s.jit_status()["launches"] > 0, "kernel": s.kernel_info()}
         if cpu:
             import oracle_lib
             c = oracle_lib.OracleSampler(workers=0)
