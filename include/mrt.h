@@ -248,6 +248,25 @@ int mrt_set_passes(mrt_ctx* ctx, uint32_t passes);
  * and collectives.  NULL restores the context's private stream. */
 int mrt_set_stream(mrt_ctx* ctx, void* cuda_stream);
 
+/* Film gather ACROSS PROCESSES of one box (one context per process and GPU, e.g. one rank per GPU under torchrun; the
+ * devices of ONE process use mrt_create_group instead).  Rather than reducing the whole 16-byte-per-pixel accumulator
+ * onto one rank (NCCL) and tone-mapping there, every rank tone-maps one band of pixels: it reads that band of EVERY
+ * rank's accumulator through CUDA IPC peer mappings (NVLink), sums in rank order and writes the u8 pixels straight into
+ * the film rank's supersampled image.  Protocol (micro_raytracer_b200/distributed.py: gather_film):
+ *   once per frame size   mrt_ipc_export on every rank -> exchange the 64-byte handles (any host channel) ->
+ *                         mrt_ipc_attach(rank, world, all accumulator handles, the film rank's image handle)
+ *   per read-out          [device-side barrier: every rank's passes are rendered] -> mrt_ipc_tonemap_band(total passes)
+ *                         on every rank -> [device-side barrier: every band is written] -> mrt_img_gathered on the film rank.
+ * The barriers are the caller's (e.g. a one-element NCCL all-reduce on the stream given to mrt_set_stream).
+ * mrt_set_frame invalidates the mappings (export / attach again). */
+#define MRT_IPC_HANDLE_BYTES 64
+int mrt_ipc_export(mrt_ctx* ctx, uint8_t accum_handle[MRT_IPC_HANDLE_BYTES], uint8_t image_handle[MRT_IPC_HANDLE_BYTES]);
+int mrt_ipc_attach(mrt_ctx* ctx, uint32_t rank, uint32_t world, const uint8_t* accum_handles /* world x 64 bytes, by rank */,
+                   const uint8_t* film_image_handle /* rank 0's image_handle */);
+int mrt_ipc_tonemap_band(mrt_ctx* ctx, uint32_t total_passes);
+/* Film rank (rank 0), after every band has been written: Lanczos3 resize of the gathered image + copy to the host. */
+int mrt_img_gathered(mrt_ctx* ctx, uint8_t* rgb);
+
 /* ≙ Sampler::img (sampler.rs:80-99): ÷passes, powf(gamma), extended-Reinhard, `as u8`,
  * Lanczos3 resize nw×nh → res.  rgb = res.0*res.1*3 bytes. */
 int mrt_img(mrt_ctx* ctx, uint8_t* rgb);
@@ -268,11 +287,10 @@ int mrt_spp_per_launch(mrt_ctx* ctx, uint32_t spp, uint32_t* current);
  * on-disk cache instead).  A compile error text is left in mrt_last_error. */
 int mrt_jit_status(mrt_ctx* ctx, uint32_t* eligible, uint32_t* compiled, uint64_t* launches, double* compile_seconds);
 
-/* How the library decided to render the scene it holds: through a scene-level BVH (scenes above ~60 box-equivalents;
- * smaller ones are unrolled into the kernel), with the pooled kernel (lanes take (pixel, sample) items from their
- * warp's pool instead of owning a pixel: scenes that search a BVH), and the feature mask of the kernel
- * (1 lights, 2 textures, 4 transmission, 8 meshes). */
-int mrt_scene_info(mrt_ctx* ctx, uint32_t* scene_bvh, uint32_t* pooled, uint32_t* features);
+/* How the library renders the scene it holds: through a scene-level BVH (scenes above ~60 box-equivalents; smaller
+ * ones are unrolled into the kernel), with the run-time specialised kernel already in use, and the feature mask of the
+ * kernel (1 lights, 2 textures, 4 transmission, 8 meshes). */
+int mrt_scene_info(mrt_ctx* ctx, uint32_t* scene_bvh, uint32_t* specialised, uint32_t* features);
 
 /* Counters of the kernels this context launched (bench.py's gpu_launches). */
 int mrt_launch_count(mrt_ctx* ctx, uint64_t* n);

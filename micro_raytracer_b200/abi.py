@@ -89,6 +89,7 @@ MRT_SYMBOLS = [
     "mrt_create", "mrt_create_group", "mrt_group_info", "mrt_device_count", "mrt_destroy", "mrt_last_error", "mrt_abi_version",
     "mrt_set_scene", "mrt_set_frame", "mrt_update_scene", "mrt_update_frame", "mrt_set_rt", "mrt_set_option", "mrt_set_partition",
     "mrt_device_seconds", "mrt_spp_per_launch", "mrt_jit_status", "mrt_scene_info",
+    "mrt_ipc_export", "mrt_ipc_attach", "mrt_ipc_tonemap_band", "mrt_img_gathered",
     "mrt_execute", "mrt_execute_async", "mrt_sync", "mrt_reset", "mrt_film_size",
     "mrt_accum", "mrt_accum_device", "mrt_set_passes", "mrt_set_stream", "mrt_img", "mrt_img_ss",
     "mrt_trace_primary", "mrt_launch_count", "mrt_fp32_peak",

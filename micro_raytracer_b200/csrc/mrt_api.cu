@@ -91,7 +91,7 @@ int launch_samples(mrt_ctx* c, uint32_t sample0, uint32_t stride, uint32_t count
         fp.n_samples = n;
         cudaError_t e = use_jit ? (c->gscene.bvh ? mrt_jit_launch_bvh(c->jit_kernel, c->gscene, fp, c->stream)
                                                  : mrt_jit_launch(c->jit_kernel, c->gscene.c, fp, c->stream))
-                                : mrt_launch_path(c->features, c->in_param, c->pool, c->pscene, &c->gscene, fp, c->stream);
+                                : mrt_launch_path(c->features, c->in_param, c->pscene, &c->gscene, fp, c->stream);
         if (e != cudaSuccess) return cuda_fail(c, e, "path kernel launch");
         if (use_jit) c->jit_launches++;
         c->launches++;
@@ -246,6 +246,14 @@ int group_collapse(mrt_ctx* c) {
         CK(cudaMemsetAsync(m->d_accum.p, 0, m->d_accum.n * sizeof(float4), m->stream));
     }
     return MRT_OK;
+}
+
+void ipc_detach(mrt_ctx* c) {
+    for (void* p : c->ipc_mapped) cudaIpcCloseMemHandle(p);
+    cudaGetLastError();
+    c->ipc_mapped.clear();
+    c->ipc_world = 0;
+    c->ipc_image = nullptr;
 }
 
 int ready_to_render(mrt_ctx* c, const char* what) {
@@ -454,6 +462,7 @@ void mrt_destroy(mrt_ctx* c) {
     c->d_accum.release(); c->d_ss.release(); c->d_out.release(); c->d_tmp.release(); c->d_rgb.release();
     c->d_wv.release(); c->d_wh.release(); c->d_lv.release(); c->d_cv.release(); c->d_lh.release(); c->d_ch.release();
     c->d_hits.release(); c->d_stage.release();
+    ipc_detach(c);
     for (auto& r : c->timing) for (auto& ev : r.ev) { if (ev.first) cudaEventDestroy(ev.first); if (ev.second) cudaEventDestroy(ev.second); }
     for (cudaEvent_t ev : c->event_pool) cudaEventDestroy(ev);
     for (cudaEvent_t ev : {c->ev0, c->ev1, c->ev_sync, c->ev_band}) if (ev) cudaEventDestroy(ev);
@@ -510,6 +519,7 @@ int mrt_set_frame(mrt_ctx* c, const mrt_frame* f) {
     CK(cudaStreamSynchronize(c->stream));
     c->have_frame = false;  // stays false if the allocation fails: no launch on a missing accumulator
     c->pending = 0;
+    ipc_detach(c);          // the buffers other processes mapped may move
     cudaError_t e = c->d_accum.alloc((size_t)nw * nh);
     if (e != cudaSuccess) return cuda_fail(c, e, "accumulator allocation");
     c->frame = *f;
@@ -666,6 +676,76 @@ int mrt_set_passes(mrt_ctx* c, uint32_t passes) {
     return MRT_OK;
 }
 
+int mrt_ipc_export(mrt_ctx* c, uint8_t* accum_handle, uint8_t* image_handle) {
+    if (!c || !accum_handle || !image_handle) return MRT_ERR_INVALID;
+    if (is_group(c)) return fail(c, MRT_ERR_INVALID, "mrt_ipc_*: one context per process and device (a group gathers its own devices)");
+    if (!c->have_frame) return fail(c, MRT_ERR_STATE, "ipc_export before set_frame");
+    static_assert(sizeof(cudaIpcMemHandle_t) == MRT_IPC_HANDLE_BYTES, "CUDA IPC handles are 64 bytes");
+    CK(cudaSetDevice(c->device));
+    CK(c->d_ss.alloc((size_t)c->nw * c->nh * 3));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->d_accum.p));
+    std::memcpy(accum_handle, &h, sizeof h);
+    CK(cudaIpcGetMemHandle(&h, c->d_ss.p));
+    std::memcpy(image_handle, &h, sizeof h);
+    return MRT_OK;
+}
+
+int mrt_ipc_attach(mrt_ctx* c, uint32_t rank, uint32_t world, const uint8_t* accum_handles, const uint8_t* film_image_handle) {
+    if (!c || !accum_handles || !film_image_handle) return MRT_ERR_INVALID;
+    if (is_group(c)) return fail(c, MRT_ERR_INVALID, "mrt_ipc_*: one context per process and device");
+    if (!c->have_frame) return fail(c, MRT_ERR_STATE, "ipc_attach before set_frame");
+    if (world == 0 || world > MRT_MAX_GROUP || rank >= world) return fail(c, MRT_ERR_INVALID, "bad rank / world (at most 16 ranks)");
+    CK(cudaSetDevice(c->device));
+    ipc_detach(c);
+    CK(c->d_ss.alloc((size_t)c->nw * c->nh * 3));
+    c->ipc_accums = PeerAccums{};
+    c->ipc_accums.n = world;
+    for (uint32_t r = 0; r < world; r++) {
+        if (r == rank) { c->ipc_accums.p[r] = c->d_accum.p; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, accum_handles + (size_t)r * MRT_IPC_HANDLE_BYTES, sizeof h);
+        void* p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { ipc_detach(c); return cuda_fail(c, e, "cudaIpcOpenMemHandle (accumulator)"); }
+        c->ipc_mapped.push_back(p);
+        c->ipc_accums.p[r] = static_cast<const float4*>(p);
+    }
+    if (rank == 0) c->ipc_image = c->d_ss.p;
+    else {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, film_image_handle, sizeof h);
+        void* p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { ipc_detach(c); return cuda_fail(c, e, "cudaIpcOpenMemHandle (film image)"); }
+        c->ipc_mapped.push_back(p);
+        c->ipc_image = static_cast<uint8_t*>(p);
+    }
+    c->ipc_rank = rank; c->ipc_world = world;
+    return MRT_OK;
+}
+
+int mrt_ipc_tonemap_band(mrt_ctx* c, uint32_t total_passes) {
+    if (!c) return MRT_ERR_INVALID;
+    if (c->ipc_world == 0) return fail(c, MRT_ERR_STATE, "ipc_tonemap_band before ipc_attach");
+    if (total_passes == 0) return fail(c, MRT_ERR_STATE, "img before any pass");
+    if (c->pending && c->have_scene) { if (int rc = flush(c, false)) return rc; }
+    CK(cudaSetDevice(c->device));
+    const uint32_t npix = c->nw * c->nh, G = c->ipc_world;
+    const uint32_t band = ((npix + G - 1u) / G + 3u) & ~3u;
+    const uint32_t first = std::min(npix, c->ipc_rank * band), count = std::min(npix - first, band);
+    c->passes_total = total_passes;
+    CK(mrt_launch_tonemap_peers(c->ipc_accums, c->ipc_image, first, count, 1.0f / (float)total_passes, c->frame.gamma, c->frame.exp, c->stream));
+    if (count) c->launches++;
+    return MRT_OK;
+}
+
+int mrt_img_gathered(mrt_ctx* c, uint8_t* rgb) {
+    if (!c || !rgb) return MRT_ERR_INVALID;
+    if (c->ipc_world == 0 || c->ipc_rank != 0) return fail(c, MRT_ERR_STATE, "img_gathered: not the film rank of an attached gather");
+    return resize_and_copy(c, rgb);
+}
+
 int mrt_img_ss(mrt_ctx* c, uint8_t* rgb) {
     if (!c || !rgb) return MRT_ERR_INVALID;
     if (int rc = tonemap_ss(c)) return rc;
@@ -728,12 +808,12 @@ int mrt_jit_status(mrt_ctx* c, uint32_t* eligible, uint32_t* compiled, uint64_t*
     return MRT_OK;
 }
 
-int mrt_scene_info(mrt_ctx* c, uint32_t* scene_bvh, uint32_t* pooled, uint32_t* features) {
+int mrt_scene_info(mrt_ctx* c, uint32_t* scene_bvh, uint32_t* specialised, uint32_t* features) {
     if (!c) return MRT_ERR_INVALID;
     if (!c->have_scene) return fail(c, MRT_ERR_STATE, "scene_info before set_scene");
     const mrt_ctx* f = film_ctx(c);
     if (scene_bvh) *scene_bvh = f->gscene.bvh ? 1u : 0u;
-    if (pooled) *pooled = f->pool ? 1u : 0u;
+    if (specialised) *specialised = f->jit_kernel ? 1u : 0u;
     if (features) *features = f->features;
     return MRT_OK;
 }

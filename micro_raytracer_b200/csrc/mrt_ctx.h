@@ -91,7 +91,6 @@ struct Knobs {
     size_t bvh_min = 60;        // MRT_BVH_MIN: BVH above this many box-equivalents
     size_t jit_cluster = 4;     // MRT_JIT_CLUSTER: box pairs per bracket in big unrolled scenes, 0 = off
     uint32_t force_features = 0;  // MRT_FORCE_FEATURES
-    int pool = 0;               // MRT_POOL=1: the pooled kernel (lanes take (pixel, sample) items from their warp's pool)
     bool mesh_via_bvh = false;  // MRT_MESH_VIA_BVH=1: scenes with a mesh go through the scene BVH whatever their size (measured: Mesh.json 2 355 vs 2 482 unrolled)
     void read() {
         if (const char* s = std::getenv("MRT_TILE")) tiled = std::atoi(s) != 0;
@@ -103,7 +102,6 @@ struct Knobs {
         if (const char* s = std::getenv("MRT_BVH_MIN")) bvh_min = (size_t)std::max(0, std::atoi(s));
         if (const char* s = std::getenv("MRT_JIT_CLUSTER")) jit_cluster = (size_t)std::max(0, std::atoi(s));
         if (const char* s = std::getenv("MRT_FORCE_FEATURES")) force_features = (uint32_t)std::atoi(s) & F_ALL;
-        if (const char* s = std::getenv("MRT_POOL")) pool = std::atoi(s);
         if (const char* s = std::getenv("MRT_MESH_VIA_BVH")) mesh_via_bvh = std::atoi(s) != 0;
     }
 };
@@ -128,6 +126,11 @@ struct mrt_ctx {
     std::vector<cudaEvent_t> event_pool;  // per device: events are recycled, not created per launch
     double unreported_s = 0.0, total_s = 0.0;
     cudaEvent_t ev_sync = nullptr, ev_band = nullptr;  // cross-device ordering inside a group
+    // film gather across processes (mrt_ipc_*): the other ranks' accumulators and the film rank's image, mapped over CUDA IPC
+    uint32_t ipc_rank = 0, ipc_world = 0;
+    std::vector<void*> ipc_mapped;      // what cudaIpcOpenMemHandle returned (closed on detach)
+    PeerAccums ipc_accums{};            // by rank; this rank's own entry is its local pointer
+    uint8_t* ipc_image = nullptr;       // the film rank's supersampled image (local on the film rank)
     uint64_t scene_hash = 0;            // content hash of the scene the context holds (mrt_update_scene)
     cudaStream_t stream = nullptr;      // the stream work is queued on
     cudaStream_t own_stream = nullptr;  // created by mrt_create
@@ -137,7 +140,6 @@ struct mrt_ctx {
 
     // scene
     bool have_scene = false, in_param = false;
-    bool pool = false;             // the scene is rendered by the pooled kernel (lanes unbound from pixels)
     uint32_t features = 0;
     ParamScene* pscene = nullptr;  // host staging copies of the kernel-parameter structs
     GlobalScene gscene{};

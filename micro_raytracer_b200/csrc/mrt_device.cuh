@@ -23,6 +23,15 @@ typedef unsigned long long uint64_t;
 
 #define MRT_E 0.0001f  // rt.rs:7
 
+// MRT_CHECKED (tools/build_variant.sh checked "-DMRT_CHECKED=1"): every table index the kernels form is checked against
+// the table's size and a violation traps the kernel (the launch then fails with a CUDA error the tests see).  This
+// pool's GPUs do not admit compute-sanitizer; the checked build run over the whole GPU test suite is the substitute.
+#ifdef MRT_CHECKED
+#define MRT_CHECK(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define MRT_CHECK(cond) do { } while (0)
+#endif
+
 enum : uint32_t {
     K_BOX = 0, K_SPHERE = 1, K_PLANE = 2, K_BOX_XF = 3, K_MESH = 4, K_NKIND = 5
 };
@@ -109,6 +118,7 @@ struct SceneCommon {
     const BvhNode* tbvh;         // triangle BVHs of all meshes (boxes relative to the instance pos); root reference in DMesh::bvh_root
     const DTriLeaf* tri_leaf;    // per triangle: the octree leaves that list it
     uint32_t n_inst, n_lights;
+    uint32_t n_tex, n_texels, n_tri, n_leaf, n_leaf_idx, n_tri_leaf, n_tbvh, n_bvh, n_mesh;  // table sizes (read by MRT_CHECK only)
     uint32_t cnt[K_NKIND];    // instances per kind
     uint32_t first[K_NKIND];  // FatInst index of the kind's first instance
     float sky[3];       // sky.color (primary miss, rt.rs:958)
@@ -171,7 +181,14 @@ __device__ __forceinline__ f3 cross(f3 a, f3 b) {
     return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
 __device__ __forceinline__ f3 fma3(f3 a, float s, f3 b) { return {fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z)}; }
+// MRT_PRECISE (ablation build, tools/build_variant.sh precise): IEEE reciprocal / square root / division and libm's
+// sincos instead of the approximate units (MUFU.RCP / MUFU.RSQ / MUFU.SIN), to separate what the approximations cost
+// in parity against the oracle from what the reference's own ill-conditioning costs ("precision ablation").
+#ifdef MRT_PRECISE
+__device__ __forceinline__ f3 normalize(f3 a) { return a * __frcp_rn(__fsqrt_rn(dot(a, a))); }  // lin.rs:64-66: self * mag().recip()
+#else
 __device__ __forceinline__ f3 normalize(f3 a) { return a * rsqrtf(dot(a, a)); }  // lin.rs:64-66
+#endif
 __device__ __forceinline__ f3 xyz(float4 v) { return {v.x, v.y, v.z}; }
 __device__ __forceinline__ f3 mulM(const float4& r0, const float4& r1, const float4& r2, f3 v) {
     return {dot(xyz(r0), v), dot(xyz(r1), v), dot(xyz(r2), v)};
@@ -182,6 +199,9 @@ __device__ __forceinline__ f3 mulXf(const Xf& x, f3 v) {
             fmaf(x.m[10], v.z, fmaf(x.m[9], v.y, x.m[8] * v.x))};
 }
 __device__ __forceinline__ float frcp(float x) {  // one MUFU.RCP
+#ifdef MRT_PRECISE
+    return __frcp_rn(x);
+#endif
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
@@ -350,7 +370,9 @@ __device__ __forceinline__ bool tri_candidate(const SceneCommon& c, const DTri& 
     const uint32_t e0 = __float_as_uint(tr.v0.w), en = __float_as_uint(tr.e0.w);
     bool cand = false;
     for (uint32_t e = 0; e < en; e++) {
+        MRT_CHECK(e0 + e < c.n_tri_leaf);
         const DTriLeaf tl = c.tri_leaf[e0 + e];
+        MRT_CHECK(tl.leaf < c.n_leaf);
         if (!leaf_slab_hit(__ldg(&c.leaf[tl.leaf].lo), __ldg(&c.leaf[tl.leaf].hi), m, om)) continue;
         if (!cand) *rf = tl.rank;
         *rl = tl.rank;
@@ -401,6 +423,7 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
     for (;;) {
         if (cur & MRT_BVH_LEAF) {
             const uint32_t ti = cur & ~MRT_BVH_LEAF;
+            MRT_CHECK(ti < mh.n_tri && mh.first_tri + ti < c.n_tri);
             const DTri* tp = &c.tri[mh.first_tri + ti];
             DTri tr;
             tr.v0 = __ldg(&tp->v0); tr.e0 = __ldg(&tp->e0); tr.e1 = __ldg(&tp->e1);
@@ -425,6 +448,7 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
                 }
             }
         } else {
+            MRT_CHECK(cur < c.n_tbvh);
             const float4 q0 = __ldg(&c.tbvh[cur].q0), q1 = __ldg(&c.tbvh[cur].q1), q2 = __ldg(&c.tbvh[cur].q2);
             const uint2 ref = __ldg(reinterpret_cast<const uint2*>(&c.tbvh[cur].ref));
             float tl, tfl, tr, tfr;
@@ -434,6 +458,7 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
             const uint32_t cl = ref.x, cr = ref.y;
             if (hl && hr) {
                 const bool left_first = tl <= tr;
+                MRT_CHECK(sp < 32);
                 if (sp < 32) { stack[sp] = left_first ? cr : cl; stack_t[sp] = left_first ? tr : tl; sp++; }
                 cur = left_first ? cl : cr;
                 continue;
@@ -502,7 +527,9 @@ __device__ __forceinline__ bool mesh_leaf_walk(const SceneCommon& c, const DMesh
                 cnt = __float_as_uint(__ldg(&c.leaf[mh.first_leaf + base + l].hi.w));
                 k = 0u;
             }
+            MRT_CHECK(first + k < c.n_leaf_idx);
             const uint32_t ti = __ldg(&c.leaf_idx[first + k]);
+            MRT_CHECK(mh.first_tri + ti < c.n_tri);
             k++;
             const DTri* tp = &c.tri[mh.first_tri + ti];
             DTri tr;
@@ -521,6 +548,7 @@ __device__ __forceinline__ bool mesh_leaf_walk(const SceneCommon& c, const DMesh
 template <bool ANY, bool WANT_T1>
 __device__ __forceinline__ bool mesh_test(const SceneCommon& c, uint32_t mesh_id, f3 o_rel, f3 d,
                                           float* t0, float* t1, int* i0, int* i1) {
+    MRT_CHECK(mesh_id < c.n_mesh);
     const DMesh mh = c.mesh[mesh_id];
     const f3 m = rcp_fixed3(d);
     const f3 om = o_rel * m;
@@ -757,6 +785,7 @@ template <uint32_t F, bool ANY, bool WANT_T1>
 __device__ __forceinline__ void bvh_leaf(Best& B, const GlobalScene& s, const RayPre& r, const RayPk& rp, uint32_t ref) {
     const SceneCommon& c = s.c;
     const uint32_t kind = ref >> 28, k = ref & 0x0fffffffu;
+    MRT_CHECK(kind < K_NKIND && kind != K_PLANE && k < c.cnt[kind]);
     float t0 = 0.f, t1 = 0.f;
     int tr0 = -1, tr1 = -1;
     bool hit;
@@ -796,8 +825,9 @@ __device__ __forceinline__ void bvh_leaf(Best& B, const GlobalScene& s, const Ra
 template <uint32_t F, bool ANY, bool WANT_T1>
 __device__ __forceinline__ void bvh_traverse(Best& B, const GlobalScene& s, const RayPre& r, const RayPk& rp) {
     uint32_t stack[32];
-    float stack_t[32];  // entry parameter of the pushed subtree's box
+    float stack_t[32];  // entry parameter of the pushed subtree's box (local memory; shared memory measured no faster)
     int sp = 0;
+    [[maybe_unused]] const uint32_t c_n_bvh = s.c.n_bvh;
     uint32_t cur = s.bvh_root;
     // next subtree; one that starts behind the best hit found since it was pushed holds nothing closer
     // ('<=': an equal t0 with a lower index must still be found)
@@ -815,6 +845,7 @@ __device__ __forceinline__ void bvh_traverse(Best& B, const GlobalScene& s, cons
             bvh_leaf<F, ANY, WANT_T1>(B, s, r, rp, cur & ~MRT_BVH_LEAF);
             if constexpr (ANY) { if (B.any) return; }
         } else {
+            MRT_CHECK(cur < c_n_bvh);
             const float4 q0 = __ldg(&s.bvh[cur].q0), q1 = __ldg(&s.bvh[cur].q1), q2 = __ldg(&s.bvh[cur].q2);
             const uint2 ref = __ldg(reinterpret_cast<const uint2*>(&s.bvh[cur].ref));
             float tl, tfl, tr, tfr;
@@ -825,6 +856,7 @@ __device__ __forceinline__ void bvh_traverse(Best& B, const GlobalScene& s, cons
             const uint32_t cl = ref.x, cr = ref.y;
             if (hl && hr) {
                 const bool left_first = tl <= tr;
+                MRT_CHECK(sp < 32);
                 if (sp < 32) { stack[sp] = left_first ? cr : cl; stack_t[sp] = left_first ? tr : tl; sp++; }
                 cur = left_first ? cl : cr;
                 continue;
@@ -832,163 +864,6 @@ __device__ __forceinline__ void bvh_traverse(Best& B, const GlobalScene& s, cons
             if (hl || hr) { cur = hl ? cl : cr; continue; }
         }
         if (!pop()) return;
-    }
-}
-
-// ---- The same search as ONE flat loop (what the kernels run; bvh_traverse + mesh_test_bvh above stay as the form
-// the bit-identity tests compare with, MRT_WALK_V1).  ncu on round 1's loop (profiles/r2_*): the node-visit block ran
-// with 12 - 14 of 32 lanes, but the leaf block with 4, the stack push with 3.7 and the pop loop with 2.5 — lanes at a
-// leaf, lanes at a node and lanes popping took turns, and a mesh instance behind a scene leaf ran its whole triangle
-// walk as one leaf step while the rest of the warp waited.  Here every turn of the loop is a NODE VISIT:
-//   * the primitives (scene level) or triangles (inside a mesh instance) behind the children of the node are tested
-//     inline, under a predicate, in the very turn that found their box — no push, no extra turn, no pop for them;
-//   * one stack entry is popped per turn, in the same turn for every lane that needs one (no inner pop loop);
-//   * a mesh instance is ENTERED: a marker goes on the stack, the lane switches to the object-space ray and keeps
-//     visiting nodes — now of the triangle BVH — in the same loop; popping the marker folds the mesh's entry / exit
-//     candidates into the scene-level best and switches back.
-// Candidates, tie rules (lexicographic (t0, instance index); first-min / last-max with candidate ranks inside a mesh)
-// and every primitive test are those of the nested form: hit ids, t0, t1 and images are bit-identical.
-#define MRT_WALK_EMPTY 0x7ffffffeu
-#define MRT_WALK_MARKER 0x7fffffffu
-#define MRT_WALK_STACK 64   // scene depth (<= 30) + marker + mesh depth (<= 30)
-template <uint32_t F, bool ANY, bool WANT_T1>
-__device__ __forceinline__ void bvh_walk(Best& B, const GlobalScene& s, const RayPre& r, const RayPk& rp) {
-    const SceneCommon& c = s.c;
-    constexpr bool MESH = (F & F_MESH) != 0 && MRT_BVH_HAS_MESH;
-    constexpr bool PRUNE_TRI = !ANY && !WANT_T1;  // inside a mesh the exit candidate may lie anywhere: no pruning when it is wanted
-    const float INF = __int_as_float(0x7f800000);
-    uint32_t stack[MRT_WALK_STACK];
-    float stack_t[MRT_WALK_STACK];
-    int sp = 0;
-    NodeRay nr = r.n;
-    const BvhNode* nodes = s.bvh;
-    bool in_mesh = false;
-    // state of the mesh instance being walked
-    f3 mo = mk(0.f, 0.f, 0.f), md = mk(0.f, 0.f, 0.f), mm = mk(0.f, 0.f, 0.f), mom = mk(0.f, 0.f, 0.f);  // object-space ray, 1/d (fixed), o * 1/d
-    uint32_t m_first_tri = 0u, m_inst = 0u;
-    float b0 = INF, b1 = -INF;
-    uint32_t r0 = 0xffffffffu, r1 = 0u;
-    int k0 = -1, k1 = -1;
-
-    auto tri_leaf = [&](uint32_t ti) {
-        const DTri* tp = &c.tri[m_first_tri + ti];
-        DTri tr;
-        tr.v0 = __ldg(&tp->v0); tr.e0 = __ldg(&tp->e0); tr.e1 = __ldg(&tp->e1);
-        float t;
-        if (tri_test(tr, mo, md, &t) && !(PRUNE_TRI && !(t <= b0))) {
-            uint32_t rf = 0xffffffffu, rl = 0u;
-            if (tri_candidate<WANT_T1>(c, tr, mm, mom, &rf, &rl)) {
-                if constexpr (ANY) { B.any = true; return; }
-                if (t < b0 || (t == b0 && rf < r0)) { b0 = t; r0 = rf; k0 = (int)ti; }
-                if constexpr (WANT_T1) { if (t > b1 || (t == b1 && rl >= r1)) { b1 = t; r1 = rl; k1 = (int)ti; } }
-            }
-        }
-    };
-    // a mesh instance behind a scene-level leaf: ray into object space, root AABB (rt.rs:708-710), then its triangle BVH.
-    // Returns the reference to continue with (the mesh's root, or EMPTY when the instance is missed / was walked inline).
-    auto enter_mesh = [&](uint32_t k) -> uint32_t {
-        if constexpr (MESH) {
-            const SlimInst e = ldg_slim(s.mesh + k);
-            f3 ol = r.o - xyz(e.a), dl = r.d;
-            if (__float_as_uint(e.b.x) != 0u) { ol = mulXf(s.mesh_m[k], ol); dl = mulXf(s.mesh_m[k], r.d); }
-            const DMesh mh = c.mesh[__float_as_uint(e.b.y)];
-            const f3 m = rcp_fixed3(dl);
-            const f3 om = ol * m;
-            if (!mesh_root_hit(mh, m, om)) return MRT_WALK_EMPTY;
-            if (mh.bvh_root == 0xffffffffu) {  // no triangle BVH (MRT_NO_MESH_BVH): the sequential leaf walk, as one step
-                float t0 = 0.f, t1 = 0.f;
-                int tr0 = -1, tr1 = -1;
-                const bool hit = mesh_leaf_walk<ANY, WANT_T1>(c, mh, ol, dl, m, om, &t0, &t1, &tr0, &tr1);
-                best_update_lex<F, ANY, WANT_T1>(B, hit, t0, t1, (int)(c.first[K_MESH] + k), tr0, tr1);
-                return MRT_WALK_EMPTY;
-            }
-            stack[sp] = MRT_WALK_MARKER; stack_t[sp] = 0.0f; sp++;
-            mo = ol; md = dl; mm = m; mom = om;
-            m_first_tri = mh.first_tri; m_inst = k;
-            b0 = INF; b1 = -INF; r0 = 0xffffffffu; r1 = 0u; k0 = -1; k1 = -1;
-            nr.bm = true_rcp3(dl, m);
-            nr.bnom = mk(-ol.x * nr.bm.x, -ol.y * nr.bm.y, -ol.z * nr.bm.z);
-            nr.bam = mk(fabsf(nr.bm.x), fabsf(nr.bm.y), fabsf(nr.bm.z));
-            nodes = c.tbvh;
-            in_mesh = true;
-            return mh.bvh_root;
-        } else {
-            (void)k;
-            return MRT_WALK_EMPTY;
-        }
-    };
-    auto is_mesh_ref = [&](uint32_t ref) -> bool { return MESH && !in_mesh && ((ref >> 28) & 7u) == K_MESH; };
-    auto leaf = [&](uint32_t ref) {  // a leaf that is NOT a mesh instance
-        if (MESH && in_mesh) tri_leaf(ref & ~MRT_BVH_LEAF);
-        else bvh_leaf<F, ANY, WANT_T1>(B, s, r, rp, ref & ~MRT_BVH_LEAF);
-    };
-
-    auto far_bound = [&]() -> float {
-        // behind this nothing can win: '<=' because an equal t0 with a lower index (rank) must still be found; inside a
-        // mesh the mesh's own entry candidate and the scene-level best both bound the search — unless the exit
-        // candidate is wanted, which may lie anywhere
-        return ANY ? INF : ((MESH && in_mesh) ? (PRUNE_TRI ? fminf(b0, B.t0) : INF) : B.t0);
-    };
-    uint32_t cur = s.bvh_root;
-    for (;;) {
-        if (cur != MRT_WALK_EMPTY) {
-            uint32_t cl = cur, cr = MRT_WALK_EMPTY, next = MRT_WALK_EMPTY;
-            float tl = 0.0f, tr = 0.0f;
-            bool hl = true, hr = false, entered = false;
-            if (cur & MRT_BVH_LEAF) {
-                // a mesh instance to enter; or a root that is a single primitive / triangle: (cl, hl) as set above
-                if (is_mesh_ref(cur)) { next = enter_mesh(cur & 0x0fffffffu); entered = true; hl = false; }
-            } else {
-                const float4 q0 = __ldg(&nodes[cur].q0), q1 = __ldg(&nodes[cur].q1), q2 = __ldg(&nodes[cur].q2);
-                const uint2 ref = __ldg(reinterpret_cast<const uint2*>(&nodes[cur].ref));
-                float tfl, tfr;
-                node_slabs(nr, q0, q1, q2, &tl, &tfl, &tr, &tfr);
-                const float bound = far_bound();
-                hl = tl <= tfl && tfl >= 0.0f && tl <= bound;
-                hr = tr <= tfr && tfr >= 0.0f && tr <= bound;
-                cl = ref.x; cr = ref.y;
-            }
-            // primitives / triangles behind the children: tested now, in this turn (one copy of the test code: the
-            // lanes whose left child is a leaf go first, then those whose right child is)
-#pragma unroll 1
-            for (int ch = 0; ch < 2; ch++) {
-                const uint32_t ref = ch ? cr : cl;
-                const bool h = ch ? hr : hl;
-                if (h && (ref & MRT_BVH_LEAF) && !is_mesh_ref(ref)) {
-                    leaf(ref);
-                    if (ch) hr = false; else hl = false;
-                }
-            }
-            if constexpr (ANY) { if (B.any) return; }
-            if (!entered) {
-                if constexpr (!ANY) {
-                    const float bound = far_bound();  // may just have come closer
-                    hl = hl && tl <= bound; hr = hr && tr <= bound;
-                }
-                if (hl && hr) {
-                    const bool left_first = tl <= tr;
-                    if (sp < MRT_WALK_STACK) { stack[sp] = left_first ? cr : cl; stack_t[sp] = left_first ? tr : tl; sp++; }
-                    next = left_first ? cl : cr;
-                } else next = hl ? cl : (hr ? cr : MRT_WALK_EMPTY);
-            }
-            cur = next;
-        }
-        if (cur == MRT_WALK_EMPTY) {  // one pop per turn
-            if (sp == 0) return;
-            --sp;
-            const uint32_t ref = stack[sp];
-            if (MESH && ref == MRT_WALK_MARKER) {  // the mesh instance is done: fold its candidates into the scene-level best
-                if constexpr (!ANY) {
-                    best_update_lex<F, ANY, WANT_T1>(B, k0 >= 0, b0, WANT_T1 ? b1 : b0, (int)(c.first[K_MESH] + m_inst), k0, WANT_T1 ? k1 : k0);
-                }
-                in_mesh = false;
-                nr = r.n;
-                nodes = s.bvh;
-                continue;
-            }
-            // a subtree that starts behind the best found since it was pushed holds nothing closer
-            if (stack_t[sp] <= far_bound()) cur = ref;
-        }
     }
 }
 
@@ -1076,11 +951,7 @@ __device__ __forceinline__ bool closest_hit(const V& sc, f3 o, f3 d, HitRec* out
 #define E_MSH(k, LE) test_mesh<F, ANY, WANT_T1, LE>(B, c, r, sc.mesh(k), sc.mesh_m(k), (int)(c.first[K_MESH] + (k)));
     if constexpr (V::kBvh) {
         if (MRT_BVH_ALWAYS || sc.s.bvh != nullptr) {  // warp-uniform: large scenes only
-#ifdef MRT_WALK_FLAT  // measured slower (round 2): Mesh 912 vs 2 355, Instance 1 856 vs 2 624, Minecraft 4 738 vs 6 266 Mpaths/s
-            bvh_walk<F, ANY, WANT_T1>(B, sc.s, r, rp);
-#else
             bvh_traverse<F, ANY, WANT_T1>(B, sc.s, r, rp);
-#endif
             for (uint32_t k = 0; k < MRT_N_PLANES(c); k++) {  // planes are infinite: brute force, same tie rule
                 const SlimInst e = sc.pln(k);
                 const float t0 = (e.b.x - dot(r.o, xyz(e.a))) * frcp(dot(r.d, xyz(e.a)));
@@ -1198,6 +1069,7 @@ __device__ __forceinline__ f3 surf_normal(const SceneCommon& c, const Surf& s, f
     if constexpr ((F & F_MESH) != 0) mesh = k == K_MESH;
     if (MRT_HAS_SPHERE && (k == K_SPHERE || (!MRT_HAS_BOX && !mesh))) n = pl * s.A.x;  // (hit - pos) / r
     else if (mesh) {
+        MRT_CHECK(tri >= 0 && __float_as_uint(s.A.x) + (uint32_t)tri < c.n_tri);
         const DTri* tp = &c.tri[__float_as_uint(s.A.x) + (uint32_t)tri];
         n = cross(xyz(__ldg(&tp->e0)), xyz(__ldg(&tp->e1)));  // rt.rs:459-466
     } else n = box_face(pl * xyz(s.A));
@@ -1240,6 +1112,7 @@ __device__ __forceinline__ float2 surf_uv(const Surf& s, f3 pl) {
 // (u == 1 runs into the next row, as in the reference); the index is clamped to the last
 // texel where the reference would panic.
 __device__ __forceinline__ float4 tex_fetch(const SceneCommon& c, uint32_t id, float2 uv) {
+    MRT_CHECK(id < c.n_tex);
     const DTex t = c.tex[id];
     if (!t.has_dat) return make_float4(0.f, 0.f, 0.f, 0.f);
     float fx = uv.x * (float)t.w, fy = uv.y * (float)t.h;
@@ -1249,6 +1122,7 @@ __device__ __forceinline__ float4 tex_fetch(const SceneCommon& c, uint32_t id, f
     const unsigned long long n = (unsigned long long)t.w * t.h;
     unsigned long long idx = (y >= n || x >= n) ? n - 1 : y * t.w + x;
     if (idx >= n) idx = n - 1;
+    MRT_CHECK(t.first + (uint32_t)idx < c.n_texels);
     return __ldg(&c.texels[t.first + (uint32_t)idx]);
 }
 
@@ -1288,7 +1162,11 @@ __device__ __forceinline__ f3 rand_normal(f3 n, float r, float u1, float u2) {
     float z = 1.0f - 2.0f * u1;
     float st = sqrtf(fmaxf(0.0f, fmaf(-z, z, 1.0f)));
     float sp, cp;
+#ifdef MRT_PRECISE
+    sincosf(u2 * 6.283185307179586f, &sp, &cp);
+#else
     __sincosf(u2 * 6.283185307179586f, &sp, &cp);
+#endif
     f3 v = mk(st * cp, st * sp, z);
     return normalize(fma3(v, r, n));
 }
@@ -1297,7 +1175,11 @@ __device__ __forceinline__ f3 rand_normal_w(f3 n, float r, uint32_t w1, uint32_t
     const float z = fmaf((float)w1, -2.0f * MRT_U32_TO_UNIT, 1.0f);
     const float st = sqrtf(fmaxf(0.0f, fmaf(-z, z, 1.0f)));
     float sp, cp;
+#ifdef MRT_PRECISE
+    sincosf((float)w2 * (6.283185307179586f * MRT_U32_TO_UNIT), &sp, &cp);
+#else
     __sincosf((float)w2 * (6.283185307179586f * MRT_U32_TO_UNIT), &sp, &cp);
+#endif
     return normalize(fma3(mk(st * cp, st * sp, z), r, n));
 }
 __device__ __forceinline__ f3 reflect3(f3 v, f3 n) { return fma3(n, -2.0f * dot(v, n), v); }  // lin.rs:68-70

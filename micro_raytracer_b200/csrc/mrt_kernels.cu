@@ -27,12 +27,6 @@ __global__ void MRT_PATH_BOUNDS path_kernel_global(const __grid_constant__ Globa
     path_body<GlobalView, F>(GlobalView{scene}, fp);
 }
 
-template <uint32_t F>
-__global__ void MRT_PATH_BOUNDS path_kernel_global_pool(const __grid_constant__ GlobalScene scene,
-                                                        const __grid_constant__ FilmParams fp) {
-    path_body_pool<GlobalView, F>(GlobalView{scene}, fp);
-}
-
 // ------------------------------------------------------------------ deterministic probe
 __global__ void __launch_bounds__(128) primary_kernel(const __grid_constant__ GlobalScene scene,
                                                       const __grid_constant__ FilmParams fp,
@@ -258,21 +252,20 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
 }
 
 template <uint32_t F>
-cudaError_t launch_path_f(bool in_param, bool pool, const ParamScene* ps, const GlobalScene* gs, const FilmParams& fp, cudaStream_t st) {
-    static_assert(MRT_PATH_BLOCK == 128 && MRT_POOL_BLOCK == MRT_PATH_BLOCK, "the tiled pixel mapping assumes blocks of four warps");
+cudaError_t launch_path_f(bool in_param, const ParamScene* ps, const GlobalScene* gs, const FilmParams& fp, cudaStream_t st) {
+    static_assert(MRT_PATH_BLOCK == 128, "the tiled pixel mapping assumes blocks of four warps");
     const dim3 grid(path_grid_blocks(fp)), block(MRT_PATH_BLOCK);
-    if (pool) path_kernel_global_pool<F><<<grid, block, 0, st>>>(*gs, fp);
-    else if (in_param) path_kernel_param<F><<<grid, block, 0, st>>>(*ps, fp);
+    if (in_param) path_kernel_param<F><<<grid, block, 0, st>>>(*ps, fp);
     else path_kernel_global<F><<<grid, block, 0, st>>>(*gs, fp);
     return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t mrt_launch_path(uint32_t features, bool in_param, bool pool, const ParamScene* ps, const GlobalScene* gs,
+cudaError_t mrt_launch_path(uint32_t features, bool in_param, const ParamScene* ps, const GlobalScene* gs,
                             const FilmParams& fp, cudaStream_t st) {
     switch (features & F_ALL) {
-#define MRT_CASE(f) case f: return launch_path_f<f>(in_param, pool, ps, gs, fp, st);
+#define MRT_CASE(f) case f: return launch_path_f<f>(in_param, ps, gs, fp, st);
         MRT_CASE(0) MRT_CASE(1) MRT_CASE(2) MRT_CASE(3) MRT_CASE(4) MRT_CASE(5) MRT_CASE(6) MRT_CASE(7)
         MRT_CASE(8) MRT_CASE(9) MRT_CASE(10) MRT_CASE(11) MRT_CASE(12) MRT_CASE(13) MRT_CASE(14) MRT_CASE(15)
 #undef MRT_CASE

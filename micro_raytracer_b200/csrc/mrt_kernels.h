@@ -24,8 +24,7 @@ struct ParamScene;
 struct GlobalScene;
 struct FilmParams;
 
-// pool: the pooled kernel (lanes unbound from pixels, mrt_path.cuh: path_body_pool); always reads the scene through `gs`
-cudaError_t mrt_launch_path(uint32_t features, bool in_param, bool pool, const ParamScene* ps, const GlobalScene* gs,
+cudaError_t mrt_launch_path(uint32_t features, bool in_param, const ParamScene* ps, const GlobalScene* gs,
                             const FilmParams& fp, cudaStream_t st);
 cudaError_t mrt_launch_primary(const GlobalScene& gs, const FilmParams& fp, mrt_hit* out, const uint32_t* obj_inst, cudaStream_t st);
 cudaError_t mrt_launch_tonemap(const float4* accum, uint8_t* out, uint32_t npix, float inv_n, float gamma, float exp, cudaStream_t st);

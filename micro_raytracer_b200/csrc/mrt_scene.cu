@@ -486,11 +486,6 @@ int mrt_scene_upload(mrt_ctx* c, const mrt_scene* s) {
     const bool want_bvh = brute_cost > bvh_min || (c->knobs.mesh_via_bvh && !by_kind[K_MESH].empty());
     bool use_bvh = want_bvh && !prim_boxes.empty() && prim_boxes_ok && prim_boxes.size() < (1u << 28) && !c->knobs.no_bvh;
     if (use_bvh) use_bvh = bvh_build_bounded(prim_boxes, &bvh_nodes, c->knobs.bvh_sah, &bvh_root);
-    // Lanes unbound from pixels (mrt_path.cuh: path_body_pool): measured and NOT a win (round 2: Mesh -5 %, Minecraft
-    // -8 %, headline -12 %; active lanes 5.8 -> 6.4 of 32: the lanes are lost inside the BVH walk, not to uneven
-    // sample budgets), so it stays an experiment knob: MRT_POOL=1.
-    const bool use_pool = c->knobs.pool > 0;
-    c->pool = use_pool;
     CK(c->d_bvh.upload(bvh_nodes));
     CK(c->d_mesh_m.upload(mesh_m));
     CK(c->d_fat.upload(fat));
@@ -619,7 +614,6 @@ int mrt_scene_upload(mrt_ctx* c, const mrt_scene* s) {
             if (binary) h += "#define MRT_JIT_EMIT_BINARY 1\n";
         }
         if (s->sky_color[0] == 0.0f && s->sky_color[1] == 0.0f && s->sky_color[2] == 0.0f) h += "#define MRT_JIT_SKY_BLACK 1\n";
-        if (use_pool) h += "#define MRT_JIT_POOL 1\n";
         h += "#define MRT_JIT_ROT " + std::to_string(rot_class) + "\n";
         h += "#define MRT_JIT_N_BOX " + std::to_string(cnt[K_BOX] + cnt[K_BOX_XF]) + "\n";
         h += "#define MRT_JIT_N_SPHERE " + std::to_string(cnt[K_SPHERE]) + "\n";
@@ -642,6 +636,9 @@ int mrt_scene_upload(mrt_ctx* c, const mrt_scene* s) {
     sc.mesh = c->d_mesh.p; sc.leaf = c->d_leaf.p; sc.leaf_idx = c->d_leaf_idx.p; sc.tri = c->d_tri.p;
     sc.tbvh = c->d_tbvh.p; sc.tri_leaf = c->d_tri_leaf.p;
     sc.n_inst = (uint32_t)fat.size();
+    sc.n_tex = (uint32_t)tex.size(); sc.n_texels = (uint32_t)texels.size(); sc.n_tri = (uint32_t)tris.size();
+    sc.n_leaf = (uint32_t)leaves.size(); sc.n_leaf_idx = (uint32_t)leaf_idx.size(); sc.n_tri_leaf = (uint32_t)tri_leaf.size();
+    sc.n_tbvh = (uint32_t)tbvh.size(); sc.n_bvh = (uint32_t)bvh_nodes.size(); sc.n_mesh = (uint32_t)meshes.size();
     sc.n_lights = s->n_lights;
     for (uint32_t k = 0; k < K_NKIND; k++) { sc.first[k] = first[k]; sc.cnt[k] = cnt[k]; }
     for (int k = 0; k < 3; k++) { sc.sky[k] = s->sky_color[k]; sc.sky_tail[k] = s->sky_color[k] * s->sky_pwr; }

@@ -75,3 +75,43 @@ def render_distributed(sampler, scene, frame, rt, spp: int, group=None, dst: int
     elif n:
         sampler.execute(scene, frame, rt, n)
     return reduce_accum(sampler, spp, group, dst, device_tensor)
+
+
+class FilmGather:
+    """Film read-out of a multi-process render WITHOUT reducing the accumulators: every rank tone-maps one band of
+    pixels, reading that band of every rank's accumulator over CUDA IPC peer mappings (NVLink), and writes the u8 pixels
+    into rank 0's supersampled image; rank 0 then resizes and copies out (include/mrt.h: mrt_ipc_*).  Against
+    reduce_accum + img() this moves 1/world of the 16-byte-per-pixel film per rank instead of all of it onto one rank,
+    and fuses the exchange into the tone-map kernel.
+
+    The sampler must share torch's current stream (sampler.set_stream(stream.cuda_stream)): the two device-side
+    barriers are one-element NCCL all-reduces queued on that stream, so nothing waits on the host."""
+
+    def __init__(self, sampler, group=None):
+        import torch
+        import torch.distributed as dist
+        self.s, self.group = sampler, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._token = torch.zeros(1, device=dev)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, sampler.ipc_export(), group=group)
+        sampler.ipc_attach(self.rank, self.world, [h[0] for h in handles], handles[0][1])
+        dist.barrier(group=group)  # nobody renders into a buffer a peer has not mapped yet
+
+    def _device_barrier(self):
+        import torch.distributed as dist
+        dist.all_reduce(self._token, group=self.group)
+
+    def bands(self, total_passes: int):
+        """Queue the gather: barrier, this rank's band, barrier.  Returns at once (everything is stream-ordered)."""
+        self.s.accum_device()          # launches whatever passes are still queued in the library
+        self._device_barrier()         # every rank's passes are rendered ...
+        self.s.ipc_tonemap_band(total_passes)
+        self._device_barrier()         # ... and every band is written
+
+    def img(self, total_passes: int) -> Optional[np.ndarray]:
+        """≙ Sampler::img of the whole job: the (res_h, res_w, 3) uint8 image on rank 0, None elsewhere."""
+        self.bands(total_passes)
+        return self.s.img_gathered() if self.rank == 0 else None

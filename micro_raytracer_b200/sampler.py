@@ -73,6 +73,10 @@ def declare(lib, prefix: str = "mrt_"):
         fn("update_frame", P, C.POINTER(abi.MrtFrame))
         fn("device_seconds", P, C.POINTER(C.c_double))
         fn("scene_info", P, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32))
+        fn("ipc_export", P, C.c_char_p, C.c_char_p)
+        fn("ipc_attach", P, u32, u32, C.c_char_p, C.c_char_p)
+        fn("ipc_tonemap_band", P, u32)
+        fn("img_gathered", P, C.POINTER(C.c_uint8))
         fn("execute_async", P, u32)
         fn("sync", P)
         fn("accum_device", P, C.POINTER(P), C.POINTER(C.c_size_t), C.POINTER(P))
@@ -306,16 +310,34 @@ class Sampler:
                 self._check(1)
         return one_pass
 
+    # -- film gather across processes (include/mrt.h: mrt_ipc_*), driven by distributed.gather_film
+    def ipc_export(self) -> Tuple[bytes, bytes]:
+        a, i = C.create_string_buffer(64), C.create_string_buffer(64)
+        self._check(self._lib.mrt_ipc_export(self._ctx, a, i))
+        return a.raw, i.raw
+
+    def ipc_attach(self, rank: int, world: int, accum_handles, film_image_handle: bytes):
+        self._check(self._lib.mrt_ipc_attach(self._ctx, int(rank), int(world), b"".join(accum_handles), film_image_handle))
+
+    def ipc_tonemap_band(self, total_passes: int):
+        self._check(self._lib.mrt_ipc_tonemap_band(self._ctx, int(total_passes)))
+
+    def img_gathered(self) -> np.ndarray:
+        w, h = self._res
+        out = np.empty((h, w, 3), np.uint8)
+        self._check(self._lib.mrt_img_gathered(self._ctx, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
     def device_seconds(self) -> float:
         t = C.c_double()
         self._check(self._lib.mrt_device_seconds(self._ctx, C.byref(t)))
         return t.value
 
     def kernel_info(self) -> dict:
-        """How the scene is rendered: scene-level BVH or unrolled, pooled kernel or one lane per pixel, feature mask."""
+        """How the scene is rendered: scene-level BVH or unrolled, run-time specialised kernel in use, feature mask."""
         b, p, f = C.c_uint32(), C.c_uint32(), C.c_uint32()
         self._check(self._lib.mrt_scene_info(self._ctx, C.byref(b), C.byref(p), C.byref(f)))
-        return {"scene_bvh": bool(b.value), "pooled": bool(p.value), "features": f.value}
+        return {"scene_bvh": bool(b.value), "specialised": bool(p.value), "features": f.value}
 
     def group_info(self) -> dict:
         n, p = C.c_uint32(), C.c_uint32()

@@ -189,26 +189,6 @@ def test_device_reduce_is_ordered_without_a_shared_stream():
     assert s.film_size()[2] == 16 and np.array_equal(s.img(r.frame), t.img(r.frame))
 
 
-# ---------------------------------------------------------------- pooled kernel (lanes unbound from pixels)
-@pytest.mark.parametrize("name,jit", [("Mesh", JIT_FORCE), ("Mesh", JIT_OFF), ("Minecraft", JIT_FORCE), ("Instance", JIT_FORCE),
-                                      ("CornellBox2", JIT_FORCE), ("dof", JIT_OFF)])
-def test_pooled_kernel_traces_the_same_paths(name, jit, monkeypatch):
-    """MRT_POOL: a lane takes (pixel, sample) items from its warp's pool instead of rendering one pixel's samples.
-    The RNG is keyed by (pixel, global sample): same paths, only the order in which a pixel's samples are summed
-    differs — and that order is itself reproducible."""
-    r = load(name, (100, 60), 1.5 if name != "Instance" else 1.0)  # partial tiles at the right and bottom edges
-    res = {}
-    for pool in ("0", "1", "1"):
-        monkeypatch.setenv("MRT_POOL", pool)
-        s = mrt.Sampler(device=0)
-        s.set_option(OPT_JIT, jit)
-        s.execute(r.scene, r.frame, r.rt, 5)
-        res.setdefault(pool, []).append(s.accum()[0])
-    assert np.array_equal(res["1"][0], res["1"][1]), "the pooled kernel must be reproducible run to run"
-    np.testing.assert_allclose(res["1"][0], res["0"][0], rtol=3e-5, atol=3e-6)
-    assert res["0"][0].max() > 0
-
-
 # ---------------------------------------------------------------- device groups (≥ 2 GPUs)
 needs2 = pytest.mark.skipif("_n_devices() < 2", reason="needs two GPUs")
 

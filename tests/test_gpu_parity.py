@@ -113,29 +113,7 @@ def test_direct_light_mode_is_deterministic_parity(pair, name, res, ssaa):
     assert np.abs(ig.astype(int) - ic.astype(int)).max() <= 1 or (np.abs(ig.astype(int) - ic.astype(int)) > 1).mean() < 2e-3
 
 
-def test_statistical_parity_cornellbox2(pair):
-    """Independent random streams (different seeds), equal spp, compared in linear space
-    (SURVEY §8c): global mean within 1 %, block-mean z-scores ~ N(0,1)."""
-    r = load("CornellBox2", (96, 96), 2.0)
-    n = 64
-    gpu = mrt.Sampler(device=0, seed=1234)
-    cpu = oracle_lib.OracleSampler(seed=99)
-    gpu.execute(r.scene, r.frame, r.rt, n)
-    cpu.execute(r.scene, r.frame, r.rt, n)
-    ag = gpu.accum()[0] / n
-    ac = cpu.accum()[0] / n
-    assert abs(ag.mean() - ac.mean()) <= 0.01 * ac.mean()
-    # per-sample sigma of 16x16 block means from the oracle's pass-to-pass spread is not
-    # available, so use the two-run difference against the pooled within-block variance
-    b = 16
-    def blocks(a):
-        h, w = a.shape[0] // b, a.shape[1] // b
-        return a[:h * b, :w * b].reshape(h, b, w, b, 3).mean(axis=(1, 3))
-    d = blocks(ag) - blocks(ac)
-    rel = np.abs(d).mean() / blocks(ac).mean()
-    assert rel < 0.06, rel
-
-
+# (statistical parity with independent random numbers, on every BASELINE config: tests/test_gpu_statistics.py)
 def test_film_tonemap_and_lanczos_match_oracle(pair):
     gpu, cpu = pair
     r = load("CornellBox2", (100, 75), 2.0)
@@ -354,7 +332,6 @@ def test_scene_bvh_returns_the_brute_force_hits(seed, monkeypatch):
     r = random_scene(seed, many=True)
     packed = mrt.pack_scene(r.scene)
     assert packed.c.n_instances > 128
-    monkeypatch.setenv("MRT_POOL", "0")  # lanes bound to pixels in both runs: same summation order (the pooled kernel has its own test)
     res = {}
     for mode in ("bvh", "brute"):
         if mode == "brute":
@@ -412,7 +389,6 @@ def test_triangle_bvh_returns_the_leaf_walk_hits(name, jit, monkeypatch):
     leaves that list the triangle is pierced (the reference's candidate set, rt.rs:707-772).  Hit ids,
     t0, t1, triangle ids and the accumulated radiance must equal the sequential leaf walk's BIT FOR BIT."""
     r = load("Mesh", res=(96, 54)) if name == "Mesh" else _mesh_scene(int(name[6:]))
-    monkeypatch.setenv("MRT_POOL", "0")  # lanes bound to pixels in both runs: same summation order
     res = {}
     for mode in ("bvh", "walk"):
         if mode == "walk":
@@ -436,7 +412,6 @@ def test_pixel_to_lane_mapping_and_bvh_splits_do_not_change_the_image(name, monk
     the surface-area heuristic or at the median (MRT_BVH_SAH).  RNG and accumulator are keyed by the pixel and
     a BVH only narrows the candidate set, so the accumulated radiance must be identical BIT FOR BIT."""
     r = load(name, (100, 60), 1.0)  # not a multiple of the 16x8 block: partial tiles at the right and bottom edges
-    monkeypatch.setenv("MRT_POOL", "0")  # lanes bound to pixels: a pixel's samples are summed in sample order whatever the mapping
     ref = None
     for tile, sah in (("1", "1"), ("0", "1"), ("1", "0")):
         monkeypatch.setenv("MRT_TILE", tile)
