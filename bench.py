@@ -18,8 +18,10 @@ devices (strong scaling) and the films are summed for the read-out.
           OUTSIDE the headline's timed region, each with the oracle's rate beside it (N = 1 only)
   cold_e2e  one-shot native `raytrace` process (start -> PNG on disk) with a cold and a warm kernel cache
 
-Launched under torchrun (the driver's way) every rank owns one GPU and the films are summed by one NCCL
-reduce.  `python bench.py --gpus N` WITHOUT torchrun renders through ONE context over N devices
+Launched under torchrun (the driver's way) every rank owns one GPU and the films are summed onto rank 0 by one NCCL
+reduce of the accumulator (0.2 ms at 8 GPUs: NVSwitch reduces in the switch).  --ipc-gather selects the alternative
+without a reduce: every rank tone-maps one band of pixels reading all ranks' accumulators over CUDA IPC peer mappings
+(distributed.FilmGather; measured 0.35 ms slower at 8 GPUs: its two device-side barriers cost more than NVLS saves).  `python bench.py --gpus N` WITHOUT torchrun renders through ONE context over N devices
 (mrt_create_group): the library splits the samples and gathers the films over NVLink peer mappings.
 
 `--impl reference` times the CPU port on all host threads (rank 0 only).
@@ -145,7 +147,8 @@ def run_reference(args, rank):
 def workload_config(args, nw, nh):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     par = ("single GPU" if args.gpus == 1 else
-           f"sample split x{args.gpus}: one process per GPU (torchrun) + one NCCL reduce of the films" if world > 1 else
+           (f"sample split x{args.gpus}: one process per GPU (torchrun) + one NCCL reduce of the films" if not args.ipc_gather else
+            f"sample split x{args.gpus}: one process per GPU (torchrun); films gathered band-wise by the tone-map kernel over CUDA IPC peer mappings") if world > 1 else
            f"sample split x{args.gpus}: ONE context over a device group (mrt_create_group), films gathered over NVLink peer mappings")
     return {"workload": f"CornellBox2.json {args.res or 1080}x{args.res or 1080} ssaa2 ({nw}x{nh} film) {args.spp} spp bounce 8 loss 0.15",
             "paths_per_step": nw * nh * args.spp, "parallelism": par,
@@ -166,6 +169,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs")
     ap.add_argument("--no-cold", action="store_true", help="skip the one-shot process timing")
+    ap.add_argument("--ipc-gather", action="store_true", help="torchrun: gather the films band-wise over CUDA IPC peer mappings instead of one NCCL reduce")
     ap.add_argument("--spp-per-launch", type=int, default=int(os.environ.get("MRT_SPP_PER_LAUNCH", "1024")),
                     help="passes rendered by one kernel launch (one accumulator read-modify-write each)")
     args = ap.parse_args()
@@ -182,7 +186,7 @@ def main():
     import torch.distributed as dist
 
     import micro_raytracer_b200 as mrt
-    from micro_raytracer_b200.distributed import passes_of_rank, reduce_accum
+    from micro_raytracer_b200.distributed import FilmGather, passes_of_rank, reduce_accum
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback")
@@ -210,10 +214,12 @@ def main():
     s._bind(packed, r.frame, r.rt)
     s.set_partition(rank, world)
     s.spp_per_launch(args.spp_per_launch)
-    acc = None
+    acc = gather = None
     if not group:
         acc_dev, _ = s.accum_device()
         acc = torch.as_tensor(acc_dev, device=dev)
+        if world > 1 and args.ipc_gather:
+            gather = FilmGather(s)     # maps every rank's accumulator into every rank (CUDA IPC), once
 
     def barrier():
         if world > 1:
@@ -225,7 +231,9 @@ def main():
     def render_step():
         s.reset()
         s.execute_async(my_passes)
-        if not group:
+        if gather:
+            gather.bands(spp)                         # every rank tone-maps its band of the summed film into rank 0's image
+        elif not group:
             reduce_accum(s, spp, device_tensor=acc)   # NCCL reduce onto rank 0 (no-op at world 1) + pass count
 
     out_img = np.empty((r.frame.res[1], r.frame.res[0], 3), np.uint8)
@@ -236,6 +244,11 @@ def main():
         s.set_partition(rank, world)
         for _ in range(my_passes):    # `for sample in 0..rt.sample { sampler.execute(..) }`, cli.rs:162
             one_pass()
+        if gather:
+            img = gather.img(spp)           # band-wise tonemap over IPC peer mappings; rank 0: Lanczos3 + D2H of the u8 image
+            if rank == 0:
+                out_img[...] = img
+            return
         if not group:
             reduce_accum(s, spp, device_tensor=acc)
         if rank == 0:
@@ -421,9 +434,11 @@ def other_configs(device, with_cpu=True):
 
 
 def cold_e2e(args, n_gpus, device):
-    """One-shot render the way a user runs it (raytrace.rs:46-48 times the whole render): the native `raytrace` binary,
-    process start -> PNG on disk, headline scene; first with an EMPTY kernel cache (NVRTC compiles in the background
-    while the generic kernel renders), then again with the cubin on disk."""
+    """One-shot render the way a user runs it: the native `raytrace` binary on the headline scene, first with an EMPTY
+    kernel cache (NVRTC compiles in the background while the generic kernel renders), then with the cubin on disk.
+    `process_s` = process start -> PNG on disk (includes CUDA driver / context start-up, which the reference does not
+    have); `render_s` = what raytrace.rs:46-48 times: Sampler::new -> image saved; its parts are listed beside it."""
+    import re
     exe = os.path.join(ROOT, "micro_raytracer_b200", "raytrace")
     if not os.path.exists(exe):
         return {"unavailable": "native raytrace binary not built"}
@@ -432,18 +447,28 @@ def cold_e2e(args, n_gpus, device):
         env = dict(os.environ, MRT_JIT_CACHE=os.path.join(td, "cache"))
         for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
             env.pop(k, None)
-        cmd = [exe, SCENE, "--sample", str(args.spp), "--device", str(device if n_gpus == 1 else 0), "--gpus", str(n_gpus), "-o", os.path.join(td, "o.png")]
+        cmd = [exe, SCENE, "-v", "--sample", str(args.spp), "--device", str(device if n_gpus == 1 else 0), "--gpus", str(n_gpus),
+               "-o", os.path.join(td, "o.png")]
         if args.res:
             cmd += ["--res", str(args.res), str(args.res)]
-        for key in ("cold_cache_s", "warm_cache_s", "warm_cache_s_2"):
+        runs = []
+        for _ in range(3):
             t0 = time.perf_counter()
             p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
             dt = time.perf_counter() - t0
             if p.returncode != 0:
                 return {"unavailable": (p.stderr or p.stdout)[-300:]}
-            out[key] = dt
+
+            def grab(pat):
+                m = re.search(pat, p.stdout)
+                return float(m.group(1)) if m else None
+            create = grab(r"created in ([0-9.eE+-]+)s")
+            runs.append({"process_s": dt, "sampler_new_s": create, "execute_loop_and_img_s": grab(r"image in host memory\): ([0-9.eE+-]+)s"),
+                         "device_s": grab(r"cli:device: ([0-9.eE+-]+)s"), "save_png_s": grab(r"cli:save: ([0-9.eE+-]+)s"),
+                         "render_s": (create or 0.0) + (grab(r"cli:done: ([0-9.eE+-]+)s") or 0.0)})
         out["png_bytes"] = os.path.getsize(os.path.join(td, "o.png"))
-    out["warm_cache_s"] = min(out["warm_cache_s"], out.pop("warm_cache_s_2"))
+    out["cold_cache"] = runs[0]
+    out["warm_cache"] = min(runs[1:], key=lambda r: r["process_s"])
     return out
 
 

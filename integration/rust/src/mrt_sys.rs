@@ -1,4 +1,4 @@
-//! FFI declarations of include/mrt.h (ABI version 1).  Field order and types are the header's.
+//! FFI declarations of include/mrt.h (ABI version 2).  Field order and types are the header's.
 #![allow(non_camel_case_types, dead_code)]
 use std::os::raw::{c_char, c_int, c_void};
 
@@ -51,6 +51,11 @@ pub enum mrt_ctx {}
 extern "C" {
     pub fn mrt_abi_version() -> c_int;
     pub fn mrt_create(out: *mut *mut mrt_ctx, device: c_int, workers: u32, n_dim: u32) -> c_int;
+    pub fn mrt_create_group(out: *mut *mut mrt_ctx, devices: *const c_int, n_devices: c_int, workers: u32, n_dim: u32) -> c_int;
+    pub fn mrt_update_scene(ctx: *mut mrt_ctx, scene: *const mrt_scene) -> c_int;
+    pub fn mrt_update_frame(ctx: *mut mrt_ctx, frame: *const mrt_frame) -> c_int;
+    pub fn mrt_sync(ctx: *mut mrt_ctx) -> c_int;
+    pub fn mrt_device_seconds(ctx: *mut mrt_ctx, total: *mut f64) -> c_int;
     pub fn mrt_destroy(ctx: *mut mrt_ctx);
     pub fn mrt_last_error(ctx: *const mrt_ctx) -> *const c_char;
     pub fn mrt_set_scene(ctx: *mut mrt_ctx, scene: *const mrt_scene) -> c_int;

@@ -1,6 +1,18 @@
 //! Drop-in replacement of the reference's src/sampler.rs: the same `Sampler::{new, execute, img}`
 //! (sampler.rs:19,28,80) over the CUDA library.  The thread pool, the per-tile HashMap merge and the
 //! tone map / Lanczos resize all happen on the GPU behind `mrt_execute` / `mrt_img`.
+//!
+//! UNCOMPILED: there is no Rust toolchain in the build image; this file is written against include/mrt.h (ABI 2) and
+//! mirrors, call for call, what micro_raytracer_b200/host/render.cpp does and what the GPU tests exercise.
+//!
+//! * `Sampler::new` makes ONE context over every GPU of the box (`mrt_create_group`): the library splits the passes
+//!   over the devices and `img` gathers their films over NVLink — cli.rs:157 / http.rs:138 need no change.
+//! * `execute` is called once per pass (cli.rs:162-163); the library queues one-pass calls and renders them in
+//!   full-length launches, so this loop reaches the batched throughput.
+//! * Nothing is cached on this side (the reference caches nothing either, sampler.rs:28): scene and frame are packed
+//!   and handed over on every call and the LIBRARY compares contents (`mrt_update_scene` / `mrt_update_frame`), so a
+//!   scene mutated in place or a new scene at an old address is picked up.  One deviation, inherited from the
+//!   library: a changed scene or frame starts a new film, where sampler.rs:60-70 would keep adding into the old one.
 use image::RgbImage;
 use std::ffi::CStr;
 use std::time::Duration;
@@ -10,9 +22,6 @@ use crate::rt::{Frame, LightKind, Material, RayTracer, RendererKind, Scene, Text
 
 pub struct Sampler {
     ctx: *mut mrt_ctx,
-    scene_key: usize,            // address of the Scene last uploaded (execute borrows it immutably, sampler.rs:28)
-    frame_key: Option<mrt_frame>,
-    rt_key: (usize, u32),
 }
 
 unsafe impl Send for Sampler {}  // one context per thread, like `&mut self` (http.rs:138,155)
@@ -114,32 +123,24 @@ impl Sampler {
     /// `workers` / `n_dim` (--worker / --dim) are accepted and ignored: the CUDA grid replaces the tile pool.
     pub fn new(workers: u32, n_dim: usize) -> Sampler {
         let mut ctx = std::ptr::null_mut();
-        let rc = unsafe { mrt_create(&mut ctx, 0, workers, n_dim as u32) };
-        if rc != MRT_OK { panic!("mrt_create: {}", last_error(std::ptr::null())); }   // Sampler::new is infallible
-        Sampler { ctx, scene_key: 0, frame_key: None, rt_key: (usize::MAX, 0) }
+        // devices = NULL, n = 0: every GPU of the box behind one context (one device gives a plain context)
+        let rc = unsafe { mrt_create_group(&mut ctx, std::ptr::null(), 0, workers, n_dim as u32) };
+        if rc != MRT_OK { panic!("mrt_create_group: {}", last_error(std::ptr::null())); }   // Sampler::new is infallible
+        Sampler { ctx }
     }
 
     fn check(&self, rc: i32) { if rc != MRT_OK { panic!("mrt: {}", last_error(self.ctx)); } }  // execute is infallible too
 
     /// One pass = one path per supersampled pixel, accumulated on the device (sampler.rs:28-78).
     pub fn execute<'a>(&mut self, scene: &'a Scene, frame: &Frame, rt: &'a RayTracer) -> Duration {
-        let key = scene as *const Scene as usize;
-        if key != self.scene_key {
-            let packed = Packed::new(scene);
-            let view = packed.view(scene);
-            self.check(unsafe { mrt_set_scene(self.ctx, &view) });
-            self.scene_key = key;
-        }
+        // the three borrows, handed over as they are NOW; identical content is a no-op inside the library
+        let packed = Packed::new(scene);
+        let view = packed.view(scene);
+        self.check(unsafe { mrt_update_scene(self.ctx, &view) });
         let f = pack_frame(frame);
-        if self.frame_key != Some(f) {
-            self.check(unsafe { mrt_set_frame(self.ctx, &f) });
-            self.frame_key = Some(f);
-        }
-        let rk = (rt.bounce, rt.loss.to_bits());
-        if rk != self.rt_key {
-            self.check(unsafe { mrt_set_rt(self.ctx, rt.bounce as u32, rt.loss, 0x5EED) });
-            self.rt_key = rk;
-        }
+        self.check(unsafe { mrt_update_frame(self.ctx, &f) });
+        self.check(unsafe { mrt_set_rt(self.ctx, rt.bounce as u32, rt.loss, 0x5EED) });
+        // queued; *seconds = device time of the launches that finished since the last call (cli.rs:164 logs it)
         let mut seconds = 0f64;
         self.check(unsafe { mrt_execute(self.ctx, 1, &mut seconds) });
         Duration::from_secs_f64(seconds)

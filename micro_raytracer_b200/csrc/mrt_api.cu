@@ -8,6 +8,8 @@
 // plain context is "its own only member".
 #include "mrt_ctx.h"
 
+#include <thread>
+
 namespace {
 
 thread_local std::string g_create_err;
@@ -403,6 +405,27 @@ int mrt_create_group(mrt_ctx** out, const int* devices, int n_devices, uint32_t 
         for (size_t j = 0; j < i; j++)
             if (devs[i] == devs[j]) { g_create_err = "mrt_create_group: a device is listed twice"; return MRT_ERR_INVALID; }
     if (devs.size() == 1) return mrt_create(out, devs[0], workers, n_dim);
+    // The first touch of a device creates its primary context (0.3 s each on a B200 box) and each peer mapping costs
+    // milliseconds: one thread per device does both, so a one-shot render on 8 GPUs waits for the slowest device, not
+    // for the sum (measured: Sampler::new over 8 GPUs 2.5 s done one after the other).
+    const bool want_p2p = !std::getenv("MRT_NO_P2P");
+    std::vector<int> peer_ok(devs.size(), 1);
+    {
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < devs.size(); i++)
+            th.emplace_back([&, i] {
+                if (cudaSetDevice(devs[i]) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) { cudaGetLastError(); peer_ok[i] = 0; return; }
+                for (size_t j = 0; j < devs.size() && want_p2p; j++) {
+                    if (i == j) continue;
+                    int can = 0;
+                    if (cudaDeviceCanAccessPeer(&can, devs[i], devs[j]) != cudaSuccess || !can) { peer_ok[i] = 0; break; }
+                    const cudaError_t pe = cudaDeviceEnablePeerAccess(devs[j], 0);
+                    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { peer_ok[i] = 0; break; }
+                }
+                cudaGetLastError();
+            });
+        for (auto& t : th) t.join();
+    }
     mrt_ctx* g = new mrt_ctx();
     for (int d : devs) {
         mrt_ctx* m = nullptr;
@@ -415,24 +438,10 @@ int mrt_create_group(mrt_ctx** out, const int* devices, int n_devices, uint32_t 
     g->coalesce = g->members[0]->coalesce;
     g->spp_per_launch = g->members[0]->spp_per_launch;
     g->jit_mode = g->members[0]->jit_mode;
-    // peer mappings, both directions of every pair (NVLink on an NVSwitch box); without them the exchange step
-    // falls back to staged copies
-    g->p2p = !std::getenv("MRT_NO_P2P");
-    for (size_t i = 0; i < devs.size() && g->p2p; i++)
-        for (size_t j = 0; j < devs.size() && g->p2p; j++) {
-            if (i == j) continue;
-            int can = 0;
-            if (cudaDeviceCanAccessPeer(&can, devs[i], devs[j]) != cudaSuccess || !can) { cudaGetLastError(); g->p2p = false; }
-        }
-    for (size_t i = 0; i < devs.size() && g->p2p; i++) {
-        cudaSetDevice(devs[i]);
-        for (size_t j = 0; j < devs.size() && g->p2p; j++) {
-            if (i == j) continue;
-            const cudaError_t pe = cudaDeviceEnablePeerAccess(devs[j], 0);
-            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) g->p2p = false;
-            cudaGetLastError();
-        }
-    }
+    // peer mappings, both directions of every pair (NVLink on an NVSwitch box; enabled by the threads above); without
+    // them the exchange step falls back to staged copies
+    g->p2p = want_p2p;
+    for (int ok : peer_ok) g->p2p = g->p2p && ok != 0;
     *out = g;
     return MRT_OK;
 }
@@ -486,7 +495,13 @@ int mrt_set_scene(mrt_ctx* c, const mrt_scene* s) {
     if (is_group(c)) {
         c->have_scene = false;
         for (mrt_ctx* m : c->members) m->normal_space = c->normal_space;
-        MEMBERS(mrt_scene_upload(m, s));
+        {   // every member packs and uploads on its own thread (independent contexts: packing is host work, ~0.1 - 1 ms each)
+            std::vector<int> rcs(c->members.size(), MRT_OK);
+            std::vector<std::thread> th;
+            for (size_t i = 0; i < c->members.size(); i++) th.emplace_back([&, i] { rcs[i] = mrt_scene_upload(c->members[i], s); });
+            for (auto& t : th) t.join();
+            for (size_t i = 0; i < rcs.size(); i++) if (rcs[i]) { c->err = c->members[i]->err; return rcs[i]; }
+        }
         c->scene_hash = c->members[0]->scene_hash;
         c->have_scene = true;
         return mrt_reset(c);

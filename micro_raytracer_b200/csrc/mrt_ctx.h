@@ -58,13 +58,12 @@ template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
-    cudaError_t upload(const std::vector<T>& h) {
-        release();
-        n = h.size();
-        const size_t bytes = std::max<size_t>(1, n) * sizeof(T);
-        cudaError_t e = cudaMalloc((void**)&p, bytes);
-        if (e != cudaSuccess) { p = nullptr; return e; }
-        if (n) e = cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice);
+    // Copies `h` to the device on `st` WITHOUT waiting: the caller synchronises the stream before `h` goes away.  An
+    // allocation of the right size is reused (a host that re-sends its scene per frame pays copies, not cudaMalloc).
+    cudaError_t upload(const std::vector<T>& h, cudaStream_t st) {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess) return e;
+        if (n) e = cudaMemcpyAsync(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice, st);
         return e;
     }
     cudaError_t alloc(size_t count) {
@@ -91,6 +90,7 @@ struct Knobs {
     size_t bvh_min = 60;        // MRT_BVH_MIN: BVH above this many box-equivalents
     size_t jit_cluster = 4;     // MRT_JIT_CLUSTER: box pairs per bracket in big unrolled scenes, 0 = off
     uint32_t force_features = 0;  // MRT_FORCE_FEATURES
+    int refine_spheres = -1;    // MRT_REFINE_SPHERES: -1 decided per scene, 0 never, 1 always (sphere hits in the reference's own arithmetic)
     bool mesh_via_bvh = false;  // MRT_MESH_VIA_BVH=1: scenes with a mesh go through the scene BVH whatever their size (measured: Mesh.json 2 355 vs 2 482 unrolled)
     void read() {
         if (const char* s = std::getenv("MRT_TILE")) tiled = std::atoi(s) != 0;
@@ -103,6 +103,7 @@ struct Knobs {
         if (const char* s = std::getenv("MRT_JIT_CLUSTER")) jit_cluster = (size_t)std::max(0, std::atoi(s));
         if (const char* s = std::getenv("MRT_FORCE_FEATURES")) force_features = (uint32_t)std::atoi(s) & F_ALL;
         if (const char* s = std::getenv("MRT_MESH_VIA_BVH")) mesh_via_bvh = std::atoi(s) != 0;
+        if (const char* s = std::getenv("MRT_REFINE_SPHERES")) refine_spheres = std::atoi(s);
     }
 };
 

@@ -119,6 +119,7 @@ struct SceneCommon {
     const DTriLeaf* tri_leaf;    // per triangle: the octree leaves that list it
     uint32_t n_inst, n_lights;
     uint32_t n_tex, n_texels, n_tri, n_leaf, n_leaf_idx, n_tri_leaf, n_tbvh, n_bvh, n_mesh;  // table sizes (read by MRT_CHECK only)
+    uint32_t refine_spheres;  // sphere hits are recomputed in the reference's own arithmetic (refine_sphere_hit)
     uint32_t cnt[K_NKIND];    // instances per kind
     uint32_t first[K_NKIND];  // FatInst index of the kind's first instance
     float sky[3];       // sky.color (primary miss, rt.rs:958)
@@ -1029,6 +1030,57 @@ __device__ __forceinline__ f3 to_local(const Surf& s, f3 hp) {
     f3 r = hp - xyz(s.P);
     return s.identity() ? r : mulM_rot(s, r);
 }
+// The winner of a closest-hit search is a sphere: its entry / exit parameters once more, in the REFERENCE'S OWN
+// ARITHMETIC — Renderer::intersect's ray (rt.rs:729-733: pos + M (o - pos)) and Sphere::intersect (rt.rs:335-359:
+// o = orig - pos, a = d.d, b = 2 o.d, c = o.o - r^2, disc = b^2 - 4ac, (-b -+ sqrt(disc)) / 2a), every operation rounded
+// on its own.  The search uses the cheaper half-b form with fused multiply-adds.  Both
+// are ill-conditioned for a small sphere seen from afar (o.o - r^2 cancels), but their rounding noise differs — and
+// that noise decides whether the NEXT ray, which starts E = 1e-4 off the computed hit point, begins inside the sphere
+// (and leaves it unseen, rt.rs:353) or outside (and may hit it again: one more bounce, one more direct-light term).
+// On Instance.json (1000 spheres of r = 0.2 seen from 5 - 9 units away) the search's own t made the image 0.85 % darker
+// than the oracle's, 5 sigma at 64 spp (tests/test_gpu_statistics.py); an oracle with the half-b form shows the same
+// shift.  Costs ~40 instructions per SPHERE HIT (not per test): nothing measurable.
+__device__ __forceinline__ float dot_rn(f3 a, f3 b) {  // lin.rs:259-264: x*x + y*y + z*z, left to right, no contraction
+    return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+// Only scenes where it can matter pay for it (SceneCommon::refine_spheres, decided by mrt_set_scene): the noise of t is
+// ~ ulp(|o - pos|^2) / (2 sqrt(disc)) ~ 1.2e-7 D^2 / r for rays of length D, and the next ray starts E = 1e-4 off the hit
+// point, so where 1.2e-7 D^2 / r stays below 4e-5 for the scene's extent D (mrt_scene.cu) neither form's noise flips the
+// side of the surface a ray starts on often enough to show (CornellBox2: 1.2e-5; Instance.json: 1.7e-4).
+#if defined(MRT_JIT)
+#define MRT_REFINE_SPHERES(c) (MRT_JIT_REFINE_SPHERES != 0)
+#else
+#define MRT_REFINE_SPHERES(c) ((c).refine_spheres != 0u)
+#endif
+__device__ __forceinline__ void refine_sphere_hit(const SceneCommon& c, f3 o, f3 d, HitRec* h) {
+    const FatInst* f = c.fat + h->inst;
+    const float4 P = __ldg(&f->P);
+    const uint32_t flags = __float_as_uint(P.w);
+    if ((flags & 0xffu) != K_SPHERE) return;
+    const f3 pos = xyz(P);
+    const float r = __ldg(&f->A).y;
+    f3 rel = mk(__fadd_rn(o.x, -pos.x), __fadd_rn(o.y, -pos.y), __fadd_rn(o.z, -pos.z));
+    f3 dl = d;
+    if (MRT_ROT != 0 && (flags & FAT_IDENT) == 0u) {
+        const float4 m0 = __ldg(&f->m0), m1 = __ldg(&f->m1), m2 = __ldg(&f->m2);
+        rel = mk(dot_rn(xyz(m0), rel), dot_rn(xyz(m1), rel), dot_rn(xyz(m2), rel));
+        dl = mk(dot_rn(xyz(m0), d), dot_rn(xyz(m1), d), dot_rn(xyz(m2), d));
+    }
+    const f3 no = mk(__fadd_rn(pos.x, rel.x), __fadd_rn(pos.y, rel.y), __fadd_rn(pos.z, rel.z));     // n_ray.orig
+    const f3 oo = mk(__fadd_rn(no.x, -pos.x), __fadd_rn(no.y, -pos.y), __fadd_rn(no.z, -pos.z));     // Sphere::intersect's o
+    const float a = dot_rn(dl, dl);
+    const float b = __fmul_rn(2.0f, dot_rn(oo, dl));
+    const float cc = __fadd_rn(dot_rn(oo, oo), -__fmul_rn(r, r));
+    const float disc = __fadd_rn(__fmul_rn(b, b), -__fmul_rn(__fmul_rn(4.0f, a), cc));
+    if (!(disc >= 0.0f)) return;  // the search saw a hit the literal form does not: keep the search's numbers
+    // (the square root and the division go through the fast units: their 1 - 2 ulp are nothing against the rounding of
+    // b^2 - 4ac, whose cancellation is what shapes the noise; IEEE versions cost 200 instructions and 8 registers)
+    const float sq = sqrtf(disc), inv = frcp(__fmul_rn(2.0f, a));
+    const float t0 = __fmul_rn(__fadd_rn(-b, -sq), inv), t1 = __fmul_rn(__fadd_rn(-b, sq), inv);
+    if (!(t0 >= 0.0f)) return;
+    h->t0 = t0; h->t1 = t1;
+}
+
 // Box::normal, rt.rs:414-445, on p = local point * 2/size: windows |p_i| in 1 +- E, checked
 // x, -x, y, -y, then — the missing `else` at :435 — an independent z test that overrides.
 // (The reference's windows are half-open, [1-E, 1+E); the open form used here differs only when

@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(128) primary_kernel(const __grid_constant__ Gl
     r.uv[0] = r.uv[1] = 0.0f;
     HitRec h;
     if (closest_hit<GlobalView, F_ALL, false, true>(sc, o, d, &h)) {
+        if (c.refine_spheres) refine_sphere_hit(c, o, d, &h);
         const FatInst* fat = c.fat + h.inst;
         Surf s;
         load_surf(fat, &s);

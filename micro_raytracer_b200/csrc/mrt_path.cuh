@@ -157,6 +157,7 @@ __device__ __forceinline__ bool path_segment(const V& sc, const FilmParams& fp, 
         path_miss(c, p, acc);
         return true;
     }
+    if (MRT_HAS_SPHERE && MRT_REFINE_SPHERES(c)) refine_sphere_hit(c, p.o, p.d, &h);
     uint32_t vis = 0;
     if constexpr ((F & F_LIGHTS) != 0) {
         const f3 hp = fma3(p.d, h.t0, p.o);

@@ -468,9 +468,9 @@ int mrt_scene_upload(mrt_ctx* c, const mrt_scene* s) {
         boxp[k].q1 = make_float4(a.a.z, b.a.z, a.a.w, b.a.w);
         boxp[k].q2 = make_float4(a.b.x, b.b.x, a.b.y, b.b.y);
     }
-    for (uint32_t k = 0; k < K_NKIND; k++) CK(c->d_slim[k].upload(by_kind[k]));
-    CK(c->d_boxp.upload(boxp));
-    CK(c->d_bxf.upload(bxf));
+    for (uint32_t k = 0; k < K_NKIND; k++) CK(c->d_slim[k].upload(by_kind[k], c->stream));
+    CK(c->d_boxp.upload(boxp, c->stream));
+    CK(c->d_bxf.upload(bxf, c->stream));
     // scene-level BVH: only for scenes too large to unroll (the specialised kernel covers <= 128 primitives)
     std::vector<BvhNode> bvh_nodes;
     uint32_t bvh_root = 0;
@@ -486,18 +486,34 @@ int mrt_scene_upload(mrt_ctx* c, const mrt_scene* s) {
     const bool want_bvh = brute_cost > bvh_min || (c->knobs.mesh_via_bvh && !by_kind[K_MESH].empty());
     bool use_bvh = want_bvh && !prim_boxes.empty() && prim_boxes_ok && prim_boxes.size() < (1u << 28) && !c->knobs.no_bvh;
     if (use_bvh) use_bvh = bvh_build_bounded(prim_boxes, &bvh_nodes, c->knobs.bvh_sah, &bvh_root);
-    CK(c->d_bvh.upload(bvh_nodes));
-    CK(c->d_mesh_m.upload(mesh_m));
-    CK(c->d_fat.upload(fat));
-    CK(c->d_tex.upload(tex));
-    CK(c->d_texels.upload(texels));
-    CK(c->d_mesh.upload(meshes));
-    CK(c->d_leaf.upload(leaves));
-    CK(c->d_leaf_idx.upload(leaf_idx));
-    CK(c->d_tri.upload(tris));
-    CK(c->d_tbvh.upload(tbvh));
-    CK(c->d_tri_leaf.upload(tri_leaf));
-    CK(c->d_obj_inst.upload(obj_inst));
+    CK(c->d_bvh.upload(bvh_nodes, c->stream));
+    CK(c->d_mesh_m.upload(mesh_m, c->stream));
+    CK(c->d_fat.upload(fat, c->stream));
+    CK(c->d_tex.upload(tex, c->stream));
+    CK(c->d_texels.upload(texels, c->stream));
+    CK(c->d_mesh.upload(meshes, c->stream));
+    CK(c->d_leaf.upload(leaves, c->stream));
+    CK(c->d_leaf_idx.upload(leaf_idx, c->stream));
+    CK(c->d_tri.upload(tris, c->stream));
+    CK(c->d_tbvh.upload(tbvh, c->stream));
+    CK(c->d_tri_leaf.upload(tri_leaf, c->stream));
+    CK(c->d_obj_inst.upload(obj_inst, c->stream));
+
+    // Do sphere hits need the reference's own arithmetic (mrt_device.cuh: refine_sphere_hit)?  Where rays of the scene's
+    // extent D give the hit distance of some sphere a rounding noise above 4e-5 (0.4 of the E = 1e-4 by which the next
+    // ray is offset): 1.2e-7 D^2 / r > 4e-5.  D = diagonal of the finite instances' bounds, doubled for the camera
+    // standing outside them (the frame is not known here): CornellBox2 1.2e-5, CornellBox 1.2e-5, Instance 1.7e-4.
+    // MRT_REFINE_SPHERES=0 / 1 forces it (A/B knob).
+    bool refine_spheres = false;
+    if (!by_kind[K_SPHERE].empty() && !prim_boxes.empty()) {
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (const PrimBox& b : prim_boxes)
+            for (int a = 0; a < 3; a++) { lo[a] = std::fmin(lo[a], b.lo[a]); hi[a] = std::fmax(hi[a], b.hi[a]); }
+        const double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        const double D2 = 4.0 * (dx * dx + dy * dy + dz * dz);
+        for (const FatInst& f : fat_k[K_SPHERE]) refine_spheres |= 1.2e-7 * D2 > 4e-5 * std::fabs((double)f.A.y);
+    }
+    if (c->knobs.refine_spheres >= 0) refine_spheres = c->knobs.refine_spheres != 0;
 
     // ---- text of the scene for the run-time specialised kernel (mrt_jit.cu); small scenes only
     if (c->jit_requested && !c->jit_header.empty()) mrt_jit_wait(c->jit_header);  // never abandon a running compile
@@ -614,6 +630,7 @@ int mrt_scene_upload(mrt_ctx* c, const mrt_scene* s) {
             if (binary) h += "#define MRT_JIT_EMIT_BINARY 1\n";
         }
         if (s->sky_color[0] == 0.0f && s->sky_color[1] == 0.0f && s->sky_color[2] == 0.0f) h += "#define MRT_JIT_SKY_BLACK 1\n";
+        h += std::string("#define MRT_JIT_REFINE_SPHERES ") + (refine_spheres ? "1\n" : "0\n");
         h += "#define MRT_JIT_ROT " + std::to_string(rot_class) + "\n";
         h += "#define MRT_JIT_N_BOX " + std::to_string(cnt[K_BOX] + cnt[K_BOX_XF]) + "\n";
         h += "#define MRT_JIT_N_SPHERE " + std::to_string(cnt[K_SPHERE]) + "\n";
@@ -636,6 +653,7 @@ int mrt_scene_upload(mrt_ctx* c, const mrt_scene* s) {
     sc.mesh = c->d_mesh.p; sc.leaf = c->d_leaf.p; sc.leaf_idx = c->d_leaf_idx.p; sc.tri = c->d_tri.p;
     sc.tbvh = c->d_tbvh.p; sc.tri_leaf = c->d_tri_leaf.p;
     sc.n_inst = (uint32_t)fat.size();
+    sc.refine_spheres = refine_spheres ? 1u : 0u;
     sc.n_tex = (uint32_t)tex.size(); sc.n_texels = (uint32_t)texels.size(); sc.n_tri = (uint32_t)tris.size();
     sc.n_leaf = (uint32_t)leaves.size(); sc.n_leaf_idx = (uint32_t)leaf_idx.size(); sc.n_tri_leaf = (uint32_t)tri_leaf.size();
     sc.n_tbvh = (uint32_t)tbvh.size(); sc.n_bvh = (uint32_t)bvh_nodes.size(); sc.n_mesh = (uint32_t)meshes.size();
@@ -670,6 +688,7 @@ int mrt_scene_upload(mrt_ctx* c, const mrt_scene* s) {
     feat |= c->knobs.force_features;
     c->features = feat;
     if (!c->jit_header.empty()) c->jit_header += "#define MRT_JIT_F " + std::to_string(feat & F_ALL) + "u\n";
+    CK(cudaStreamSynchronize(c->stream));  // the uploads above are asynchronous and read this function's local arrays
     c->scene_hash = mrt_scene_hash(s, c->normal_space);
     c->have_scene = true;
     return MRT_OK;

@@ -22,8 +22,9 @@ static double raytrace(const CliArgs& a, const Render& render, const Logger& log
     const std::string out = a.output.value_or("out.png");
     std::vector<int> devices;
     for (int g = 0; g < a.gpus; g++) devices.push_back(a.device + g);
+    const double t_new = now();
     Sampler sampler(devices, (uint32_t)a.worker.value_or(24), (uint32_t)a.dim.value_or(64), a.seed);  // cli.rs:157
-    if (log && a.gpus > 1) log("cli:sampler: on " + std::to_string(sampler.n_devices()) + " gpus");
+    if (log) log("cli:sampler: on " + std::to_string(sampler.n_devices()) + " gpus, created in " + std::to_string(now() - t_new) + "s");
     const double t0 = now();
     for (uint32_t n = 0; n < render.rt.sample; n++) {  // cli.rs:162
         const double dt = sampler.execute(render.scene, render.frame, render.rt);
@@ -31,8 +32,10 @@ static double raytrace(const CliArgs& a, const Render& render, const Logger& log
         if (a.update) save_image(sampler.img(render.frame), out);  // cli.rs:166-169
     }
     const Image im = sampler.img(render.frame);  // cli.rs:173: renders whatever is still queued
-    if (log) log("cli:device: " + std::to_string(sampler.device_seconds()) + "s in path kernels");
+    const double t1 = now();
+    if (log) log("cli:device: " + std::to_string(sampler.device_seconds()) + "s in path kernels; render (first execute -> image in host memory): " + std::to_string(t1 - t0) + "s");
     save_image(im, out);
+    if (log) log("cli:save: " + std::to_string(now() - t1) + "s");
     return now() - t0;
 }
 

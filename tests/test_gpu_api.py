@@ -251,7 +251,7 @@ def test_group_context_errors():
 
 @needs2
 def test_group_scales_the_headline_render():
-    """Strong scaling through ONE context: the headline film at 256 spp on all devices vs one."""
+    """Strong scaling through ONE context: the headline render (1024 spp, the reference's loop) on all devices vs one."""
     n_dev = min(_n_devices(), 8)
     r = load("CornellBox2")
     t = {}
@@ -262,8 +262,8 @@ def test_group_scales_the_headline_render():
         s.img(r.frame)
         s.reset()
         t0 = time.perf_counter()
-        for _ in range(256):
+        for _ in range(1024):
             s.execute(r.scene, r.frame, r.rt)
         s.img(r.frame)
         t[len(devs)] = time.perf_counter() - t0
-    assert t[n_dev] < t[1] / (0.85 * n_dev), t
+    assert t[n_dev] < t[1] / (0.8 * n_dev), t

@@ -12,5 +12,5 @@ nvcc $FL -c mrt_api.cu -o $D/a.o &
 nvcc $FL -c mrt_scene.cu -o $D/s.o &
 nvcc $FL -c mrt_jit.cu -o $D/j.o &
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../scratch/libmrt_$1.so $D/k.o $D/a.o $D/s.o $D/j.o -ldl
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../scratch/libmrt_$1.so $D/k.o $D/a.o $D/s.o $D/j.o -ldl -lpthread
 grep -A3 "path_kernel_paramILj0E" $D/ptxas.log | grep -E "registers|spill" | tr '\n' ' '; echo " <- $1"

@@ -8,6 +8,7 @@
 #define MRT_JIT_MINBLOCKS 8
 #define MRT_JIT_EMIT_BINARY 1
 #define MRT_JIT_SKY_BLACK 1
+#define MRT_JIT_REFINE_SPHERES 0
 #define MRT_JIT_ROT 0
 #define MRT_JIT_N_BOX 0
 #define MRT_JIT_N_SPHERE 0
