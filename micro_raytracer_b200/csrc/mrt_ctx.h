@@ -176,7 +176,7 @@ struct mrt_ctx {
     // run-time scene specialisation (mrt_jit.cu)
     uint32_t jit_mode = MRT_JIT_AUTO;   // MRT_OPT_JIT
     std::string jit_header;             // "" = scene not eligible
-    cudaKernel_t jit_kernel = nullptr;  // compiled for jit_header
+    const MrtJitKernels* jit_kernel = nullptr;  // compiled for jit_header (both entry points)
     bool jit_requested = false, jit_failed = false, jit_from_disk = false;
     double jit_seconds = 0.0;
     std::string jit_err;

@@ -186,14 +186,23 @@ __device__ __forceinline__ void thread_pixel(const FilmParams& fp, uint32_t* px,
 }
 
 // The megakernel body, one thread per supersampled pixel: the lane renders its pixel's samples back to back.
-template <class V, uint32_t F>
+// LENS: how camera rays start — LENS_PINHOLE / LENS_THIN compile one case in (the specialised kernel has an entry point
+// for each), LENS_ANY decides at run time (the offline-built generic kernels).
+enum : int { LENS_PINHOLE = 0, LENS_THIN = 1, LENS_ANY = 2 };
+template <class V, uint32_t F, int LENS = LENS_ANY>
 __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
     uint32_t px, py;
     thread_pixel(fp, &px, &py);
     if (px >= fp.nw || py >= fp.nh || fp.n_samples == 0u) return;
     const uint32_t pix = py * fp.nw + px;
-    const f3 q = pixel_focus_vec(fp, px, py);
+    f3 q = pixel_focus_vec(fp, px, py);
     const uint32_t cam_seed = cam_hash_seed(pix, fp.key);
+    // Pinhole camera (aperture 0, the default of every example scene but dof.json): the lens jitter is (u - 0.5) * 0, so
+    // every sample of a pixel starts with the same ray.  Its direction is computed once, here, by the very same
+    // arithmetic (camera_ray with zero jitter: bit-identical images), and starting a path shrinks from ~50 instructions
+    // — lens hash, normalisation, camera rotation; run by ~4 lanes of the warp in 96 % of the loop's iterations — to 11.
+    const bool pinhole = LENS == LENS_PINHOLE || (LENS == LENS_ANY && fp.aprt == 0.0f);  // warp-uniform
+    if (pinhole) { f3 o0; camera_ray(fp, q, 0.5f, 0.5f, &o0, &q); }  // q := the pixel's ray direction
 
     f3 acc = mk(0.f, 0.f, 0.f);
     PathState p;
@@ -212,8 +221,17 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
     for (;;) {
         if (p.bounce == MRT_NEED_PATH) {
             if (j >= fp.n_samples) break;
-            const float2 u = rng_cam(cam_seed, fp.sample0 + j * fp.sample_stride);
-            camera_ray(fp, q, u.x, u.y, &p.o, &p.d);
+            if (pinhole) {
+                // (the empty asm keeps the origin's three FFMA here: hoisted out of the loop it would hold three more
+                // registers for the whole kernel, 56 instead of 48 = one resident block per SM less)
+                float dx = q.x, dy = q.y, dz = q.z;
+                asm volatile("" : "+f"(dx), "+f"(dy), "+f"(dz));
+                p.d = mk(dx, dy, dz);
+                p.o = fma3(p.d, MRT_E, mk(fp.cam_pos[0], fp.cam_pos[1], fp.cam_pos[2]));  // Ray::cast_default, rt.rs:555-557
+            } else {
+                const float2 u = rng_cam(cam_seed, fp.sample0 + j * fp.sample_stride);
+                camera_ray(fp, q, u.x, u.y, &p.o, &p.d);
+            }
             p.T = mk(1.f, 1.f, 1.f);
             p.pwr = 1.0f;
             p.bounce = 0;

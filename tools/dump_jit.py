@@ -13,7 +13,7 @@ from util import load
 r = load(sys.argv[1], (96, 54), 1.0)
 s = mrt.Sampler(device=0)
 s.set_option(2, 2)
-s.execute(r.scene, r.frame, r.rt, 1)
+s.execute(r.scene, r.frame, r.rt, 2)  # a batched call: launches (and, with MRT_JIT_FORCE, compiles) at once
 print(sys.argv[1], s.jit_status())
 """ % (ROOT, os.path.join(ROOT, "tests"))
 for name in ["Default", "CornellBox", "CornellBox2", "dof", "Mesh", "Minecraft", "Instance"]:
