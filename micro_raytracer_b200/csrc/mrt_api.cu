@@ -91,8 +91,8 @@ int launch_samples(mrt_ctx* c, uint32_t sample0, uint32_t stride, uint32_t count
         fp.sample0 = s0;
         fp.sample_stride = stride;
         fp.n_samples = n;
-        cudaError_t e = use_jit ? (c->gscene.bvh ? mrt_jit_launch_bvh(c->jit_kernel, c->gscene, fp, c->stream)
-                                                 : mrt_jit_launch(c->jit_kernel, c->gscene.c, fp, c->stream))
+        cudaError_t e = use_jit ? (c->gscene.bvh ? mrt_jit_launch_bvh(c->jit_kernel, c->gscene, fp, c->stream, c->knobs.pinhole)
+                                                 : mrt_jit_launch(c->jit_kernel, c->gscene.c, fp, c->stream, c->knobs.pinhole))
                                 : mrt_launch_path(c->features, c->in_param, c->pscene, &c->gscene, fp, c->stream);
         if (e != cudaSuccess) return cuda_fail(c, e, "path kernel launch");
         if (use_jit) c->jit_launches++;

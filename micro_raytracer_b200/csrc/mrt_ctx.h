@@ -91,11 +91,13 @@ struct Knobs {
     size_t jit_cluster = 4;     // MRT_JIT_CLUSTER: box pairs per bracket in big unrolled scenes, 0 = off
     uint32_t force_features = 0;  // MRT_FORCE_FEATURES
     int refine_spheres = -1;    // MRT_REFINE_SPHERES: -1 decided per scene, 0 never, 1 always (sphere hits in the reference's own arithmetic)
+    bool pinhole = true;        // MRT_NO_PINHOLE: frames with aperture 0 go through the thin-lens entry point too (the A/B of the bit-identity test)
     bool mesh_via_bvh = false;  // MRT_MESH_VIA_BVH=1: scenes with a mesh go through the scene BVH whatever their size (measured: Mesh.json 2 355 vs 2 482 unrolled)
     void read() {
         if (const char* s = std::getenv("MRT_TILE")) tiled = std::atoi(s) != 0;
         if (const char* s = std::getenv("MRT_BVH_SAH")) bvh_sah = std::atoi(s) != 0;
         mesh_bvh = !std::getenv("MRT_NO_MESH_BVH");
+        pinhole = !std::getenv("MRT_NO_PINHOLE");
         no_bvh = std::getenv("MRT_NO_BVH") != nullptr;
         force_global = std::getenv("MRT_FORCE_GLOBAL_SCENE") != nullptr;
         if (const char* s = std::getenv("MRT_JIT_MINBLOCKS")) jit_minblocks_env = *s != 0;

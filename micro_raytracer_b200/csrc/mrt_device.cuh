@@ -87,6 +87,7 @@ static_assert(sizeof(FatInst) == 128, "FatInst must be one cache line");
 // index within the kind's table; mesh BVH: triangle index within the mesh), else the index of the child node.
 // One primitive per leaf, so leaves need no node at all.
 struct BvhNode { float4 q0, q1, q2; uint4 ref; };
+static_assert(sizeof(BvhNode) == 64, "a BVH node is read as two 32-byte words");
 #define MRT_BVH_LEAF 0x80000000u
 struct DLight { float4 v_kind; float4 color_pwr; };  // v.xyz (pos or unit -dir), w = kind bits ; color.rgb, pwr
 struct DTex { uint32_t w, h, first, has_dat; };      // texel offset into the float4 texel array
@@ -94,7 +95,8 @@ struct DMeshLeaf { float4 lo, hi; };                  // leaf box relative to in
 struct DMesh { uint32_t first_leaf, n_leaf, first_tri, n_tri; float half[3]; uint32_t bvh_root; };  // half = half extents of the root AABB; bvh_root = 0xffffffff: no triangle BVH
 // v0, e0 = v1 - v0, e1 = v2 - v0 (object space, before + pos); v0.w / e0.w (bits) = first entry / entry count of the
 // triangle's DTriLeaf list
-struct DTri { float4 v0, e0, e1; };
+struct DTri { float4 v0, e0, e1, pad; };  // 64 bytes: read as one 32-byte word (v0, e0) + e1
+static_assert(sizeof(DTri) == 64, "DTri is read with 32-byte loads");
 // One octree leaf that lists a triangle: `leaf` indexes SceneCommon::leaf, `rank` is the position of this
 // occurrence in the reference's candidate sequence (leaf order, then list order).  Ascending rank per triangle.
 struct DTriLeaf { uint32_t leaf, rank; };
@@ -208,6 +210,22 @@ __device__ __forceinline__ float frcp(float x) {  // one MUFU.RCP
     return r;
 }
 
+// 256-bit read-only load (sm_100: LDG.E.256, ld.global.nc.v8): the BVH kernels are bound by the L1 data pipe, not by issue
+// slots (ncu, Instance.json: l1tex__data_pipe_lsu_wavefronts 82 % of peak at 64 % issue) — every lane of a divergent walk reads
+// its own node, so a load instruction costs one wavefront per active lane whatever its width; 32 bytes per instruction halve
+// the wavefronts of a node visit (64 B), of a leaf (32 B) and of the hit's FatInst rows.  `p` must be 32-byte aligned.
+struct f8 { float4 lo, hi; };
+__device__ __forceinline__ f8 ldg256(const void* p) {
+    f8 r;
+#ifdef MRT_NO_LD256
+    r.lo = __ldg(reinterpret_cast<const float4*>(p)); r.hi = __ldg(reinterpret_cast<const float4*>(p) + 1);
+#else
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p));
+#endif
+    return r;
+}
+
 // Packed f32x2 arithmetic (sm_100 FFMA2): one issue slot for two FMAs.  Measured on B200
 // (tools/microbench.cu): same 74 TFLOP/s as FFMA in half the issue slots; operands may be
 // register pairs, uniform-register pairs or a scalar broadcast to both lanes.
@@ -304,7 +322,7 @@ struct ParamView {
     __device__ __forceinline__ SlimInst mesh(uint32_t k) const { return s.mesh[k]; }
     __device__ __forceinline__ const Xf& mesh_m(uint32_t k) const { return s.mesh_m[k]; }
 };
-__device__ __forceinline__ SlimInst ldg_slim(const SlimInst* p) { return {__ldg(&p->a), __ldg(&p->b)}; }
+__device__ __forceinline__ SlimInst ldg_slim(const SlimInst* p) { const f8 v = ldg256(p); return {v.lo, v.hi}; }
 struct GlobalView {
     static constexpr bool kParam = false;
     static constexpr bool kJit = false;
@@ -400,8 +418,7 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
     float b0 = INF, b1 = -INF;
     uint32_t r0 = 0xffffffffu, r1 = 0u;
     int k0 = -1, k1 = -1;
-    uint32_t stack[32];
-    float stack_t[32];  // entry parameter of the pushed subtree's box
+    uint2 stack[32];  // (reference, entry parameter of the pushed subtree's box): one 8-byte word per entry
     int sp = 0;
     // Two slab tests.  `leaf_slab` is the reference's Box::intersect on an octree leaf, 1/E quirk included
     // (a zero direction component behaves like a slope of 1/E, so a leaf the ray runs inside of can still be
@@ -427,7 +444,7 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
             MRT_CHECK(ti < mh.n_tri && mh.first_tri + ti < c.n_tri);
             const DTri* tp = &c.tri[mh.first_tri + ti];
             DTri tr;
-            tr.v0 = __ldg(&tp->v0); tr.e0 = __ldg(&tp->e0); tr.e1 = __ldg(&tp->e1);
+            { const f8 ve = ldg256(tp); tr.v0 = ve.lo; tr.e0 = ve.hi; tr.e1 = __ldg(&tp->e1); }
             float t;
             if (tri_test(tr, o_rel, d, &t) && !(PRUNE && !(t <= b0))) {
                 // is the triangle a candidate?  first / last pierced leaf that lists it
@@ -436,7 +453,8 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
                 bool cand = false;
                 for (uint32_t e = 0; e < en; e++) {
                     const DTriLeaf tl = c.tri_leaf[e0 + e];
-                    if (!leaf_slab(__ldg(&c.leaf[tl.leaf].lo), __ldg(&c.leaf[tl.leaf].hi))) continue;
+                    const f8 lh = ldg256(&c.leaf[tl.leaf]);  // lo, hi
+                    if (!leaf_slab(lh.lo, lh.hi)) continue;
                     if (!cand) rf = tl.rank;
                     rl = tl.rank;
                     cand = true;
@@ -450,8 +468,9 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
             }
         } else {
             MRT_CHECK(cur < c.n_tbvh);
-            const float4 q0 = __ldg(&c.tbvh[cur].q0), q1 = __ldg(&c.tbvh[cur].q1), q2 = __ldg(&c.tbvh[cur].q2);
-            const uint2 ref = __ldg(reinterpret_cast<const uint2*>(&c.tbvh[cur].ref));
+            const f8 n01 = ldg256(&c.tbvh[cur].q0), n23 = ldg256(&c.tbvh[cur].q2);
+            const float4 q0 = n01.lo, q1 = n01.hi, q2 = n23.lo;
+            const uint2 ref = make_uint2(__float_as_uint(n23.hi.x), __float_as_uint(n23.hi.y));
             float tl, tfl, tr, tfr;
             node_slabs(nr, q0, q1, q2, &tl, &tfl, &tr, &tfr);
             bool hl = !(tl > tfl || tfl < 0.0f), hr = !(tr > tfr || tfr < 0.0f);
@@ -460,7 +479,7 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
             if (hl && hr) {
                 const bool left_first = tl <= tr;
                 MRT_CHECK(sp < 32);
-                if (sp < 32) { stack[sp] = left_first ? cr : cl; stack_t[sp] = left_first ? tr : tl; sp++; }
+                if (sp < 32) { stack[sp] = make_uint2(left_first ? cr : cl, __float_as_uint(left_first ? tr : tl)); sp++; }
                 cur = left_first ? cl : cr;
                 continue;
             }
@@ -470,7 +489,8 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
         bool more = false;
         while (sp > 0) {
             --sp;
-            if (!PRUNE || stack_t[sp] <= b0) { cur = stack[sp]; more = true; break; }
+            const uint2 e = stack[sp];
+            if (!PRUNE || __uint_as_float(e.y) <= b0) { cur = e.x; more = true; break; }
         }
         if (!more) break;
     }
@@ -745,7 +765,12 @@ __device__ __forceinline__ void best_update_lex(Best& B, bool hit, float t0, flo
     if constexpr (ANY) {
         B.any |= hit;
     } else {
+#ifdef MRT_LEX_BRANCHY
         if (hit && (t0 < B.t0 || (t0 == B.t0 && idx < B.bi))) {
+#else
+        // ('&' / '|': with '&&' / '||' the compiler emits three divergent branches for this test)
+        if (hit & ((t0 < B.t0) | ((t0 == B.t0) & (idx < B.bi)))) {
+#endif
             B.t0 = t0; B.bi = idx;
             if constexpr (WANT_T1) B.t1 = t1;
             if constexpr ((F & F_MESH) != 0) { B.tr0 = tr0; B.tr1 = tr1; }
@@ -785,7 +810,9 @@ __device__ __forceinline__ bool bracket_hit(const RayPre& r, float4 lo, float4 h
 template <uint32_t F, bool ANY, bool WANT_T1>
 __device__ __forceinline__ void bvh_leaf(Best& B, const GlobalScene& s, const RayPre& r, const RayPk& rp, uint32_t ref) {
     const SceneCommon& c = s.c;
-    const uint32_t kind = ref >> 28, k = ref & 0x0fffffffu;
+    // (table indices stay below 2^24 — the scene BVH is only built for fewer primitives, mrt_scene.cu — so the byte offset
+    // k * sizeof(entry) is formed in 32 bits: one IMAD.WIDE instead of a 64-bit shift, 8 -> 3 instructions per leaf visit)
+    const uint32_t kind = ref >> 28, k = ref & 0x00ffffffu;
     MRT_CHECK(kind < K_NKIND && kind != K_PLANE && k < c.cnt[kind]);
     float t0 = 0.f, t1 = 0.f;
     int tr0 = -1, tr1 = -1;
@@ -825,8 +852,9 @@ __device__ __forceinline__ void bvh_leaf(Best& B, const GlobalScene& s, const Ra
 }
 template <uint32_t F, bool ANY, bool WANT_T1>
 __device__ __forceinline__ void bvh_traverse(Best& B, const GlobalScene& s, const RayPre& r, const RayPk& rp) {
-    uint32_t stack[32];
-    float stack_t[32];  // entry parameter of the pushed subtree's box (local memory; shared memory measured no faster)
+    // (reference, entry parameter of the pushed subtree's box) in one 8-byte word: one STL.64 per push, one LDL.64 per
+    // popped entry (local memory; shared memory measured no faster)
+    uint2 stack[32];
     int sp = 0;
     [[maybe_unused]] const uint32_t c_n_bvh = s.c.n_bvh;
     uint32_t cur = s.bvh_root;
@@ -837,7 +865,8 @@ __device__ __forceinline__ void bvh_traverse(Best& B, const GlobalScene& s, cons
     auto pop = [&]() -> bool {
         while (sp > 0) {
             --sp;
-            if (ANY || stack_t[sp] <= B.t0) { cur = stack[sp]; return true; }
+            const uint2 e = stack[sp];
+            if (ANY || __uint_as_float(e.y) <= B.t0) { cur = e.x; return true; }
         }
         return false;
     };
@@ -847,8 +876,9 @@ __device__ __forceinline__ void bvh_traverse(Best& B, const GlobalScene& s, cons
             if constexpr (ANY) { if (B.any) return; }
         } else {
             MRT_CHECK(cur < c_n_bvh);
-            const float4 q0 = __ldg(&s.bvh[cur].q0), q1 = __ldg(&s.bvh[cur].q1), q2 = __ldg(&s.bvh[cur].q2);
-            const uint2 ref = __ldg(reinterpret_cast<const uint2*>(&s.bvh[cur].ref));
+            const f8 n01 = ldg256(&s.bvh[cur].q0), n23 = ldg256(&s.bvh[cur].q2);
+            const float4 q0 = n01.lo, q1 = n01.hi, q2 = n23.lo;
+            const uint2 ref = make_uint2(__float_as_uint(n23.hi.x), __float_as_uint(n23.hi.y));
             float tl, tfl, tr, tfr;
             node_slabs(r.n, q0, q1, q2, &tl, &tfl, &tr, &tfr);
             // '<=': an equal t0 with a lower index must still be found
@@ -858,7 +888,7 @@ __device__ __forceinline__ void bvh_traverse(Best& B, const GlobalScene& s, cons
             if (hl && hr) {
                 const bool left_first = tl <= tr;
                 MRT_CHECK(sp < 32);
-                if (sp < 32) { stack[sp] = left_first ? cr : cl; stack_t[sp] = left_first ? tr : tl; sp++; }
+                if (sp < 32) { stack[sp] = make_uint2(left_first ? cr : cl, __float_as_uint(left_first ? tr : tl)); sp++; }
                 cur = left_first ? cl : cr;
                 continue;
             }
@@ -1007,13 +1037,15 @@ __device__ __forceinline__ f3 mulM_rot(const Surf& s, f3 v) {
 #endif
 }
 __device__ __forceinline__ void load_surf(const FatInst* f, Surf* s) {
-    s->P = __ldg(&f->P);
-    s->A = __ldg(&f->A);
+    const f8 pa = ldg256(f);  // P, A
+    s->P = pa.lo;
+    s->A = pa.hi;
     // rows only when rotated or textured (the texture ids live in .w)
     const bool rows = (MRT_ROT == 0) ? (s->flags() & FAT_TEX) != 0u : (s->flags() & (FAT_IDENT | FAT_TEX)) != FAT_IDENT;
     if (rows) {
-        s->m0 = __ldg(&f->m0);
-        s->m1 = __ldg(&f->m1);
+        const f8 m01 = ldg256(&f->m0);  // m0, m1
+        s->m0 = m01.lo;
+        s->m1 = m01.hi;
         s->m2 = __ldg(&f->m2);
     }
 #ifndef MRT_JIT
@@ -1089,7 +1121,9 @@ __device__ __forceinline__ void refine_sphere_hit(const SceneCommon& c, f3 o, f3
 __device__ __forceinline__ f3 box_face(f3 p) {
     // windowed axes get a score that encodes the reference's priority (z over x over y); the rest
     // score e = |p_i| - 1 (<= 0 on the surface), so the largest score also picks the nearest face
-    // when no window matches.  Branch-free.
+    // when no window matches.  Branch-free.  (Testing the three windows directly and keeping the nearest-face rule
+    // for the ~1e-7 of hits without one is fewer operations on paper, but the compiler turns it into a chain of
+    // divergent branches: 331 instead of 317 instructions per loop iteration of the headline kernel.)
     const float ex = fabsf(p.x) - 1.0f, ey = fabsf(p.y) - 1.0f, ez = fabsf(p.z) - 1.0f;
     const float sz = fabsf(ez) < MRT_E ? 3e30f : ez;
     const float sx = fabsf(ex) < MRT_E ? 2e30f : ex;
@@ -1186,11 +1220,12 @@ struct Mat {
 // material getters, rt.rs:811-863, all maps fetched at the same uv
 template <uint32_t F>
 __device__ __forceinline__ void load_mat(const SceneCommon& c, const FatInst* f, const Surf& s, f3 pl, Mat* m) {
-    const float4 ae = __ldg(&f->C);
 #if defined(MRT_JIT) && defined(MRT_JIT_UNIFORM_R)
+    const float4 ae = __ldg(&f->C);
     const float4 r = make_float4(MRT_JIT_UNIFORM_R);  // every material of the scene has these rough/metal/glass/opacity: literals
 #else
-    const float4 r = __ldg(&f->R);
+    const f8 cr = ldg256(&f->C);  // C, R
+    const float4 ae = cr.lo, r = cr.hi;
 #endif
     m->color = xyz(ae); m->emit = ae.w;
     m->rough = r.x; m->metal = r.y; m->glass = r.z; m->opacity = r.w; m->metal_raw = r.y;

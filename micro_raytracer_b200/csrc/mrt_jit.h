@@ -10,7 +10,7 @@
 // same ray: no lens code at all), `thin` for thin-lens frames.
 struct MrtJitKernels {
     cudaKernel_t thin = nullptr, pinhole = nullptr;
-    cudaKernel_t pick(const FilmParams& fp) const { return fp.aprt == 0.0f ? pinhole : thin; }
+    cudaKernel_t pick(const FilmParams& fp, bool allow_pinhole) const { return allow_pinhole && fp.aprt == 0.0f ? pinhole : thin; }
 };
 struct MrtJitInfo { bool pending = false; bool from_disk = false; double seconds = 0.0; std::string err; };
 
@@ -22,6 +22,6 @@ struct MrtJitInfo { bool pending = false; bool from_disk = false; double seconds
 const MrtJitKernels* mrt_jit_kernel(const std::string& scene_header, int wait_ms, MrtJitInfo* info);
 // Blocks until a compile started for `scene_header` (if any) is over.
 void mrt_jit_wait(const std::string& scene_header);
-cudaError_t mrt_jit_launch(const MrtJitKernels* k, const SceneCommon& scene, const FilmParams& fp, cudaStream_t st);
+cudaError_t mrt_jit_launch(const MrtJitKernels* k, const SceneCommon& scene, const FilmParams& fp, cudaStream_t st, bool allow_pinhole = true);
 // the kernel of a BVH scene (header with MRT_JIT_BVH) takes the whole GlobalScene
-cudaError_t mrt_jit_launch_bvh(const MrtJitKernels* k, const GlobalScene& scene, const FilmParams& fp, cudaStream_t st);
+cudaError_t mrt_jit_launch_bvh(const MrtJitKernels* k, const GlobalScene& scene, const FilmParams& fp, cudaStream_t st, bool allow_pinhole = true);

@@ -53,15 +53,16 @@ __device__ __forceinline__ void path_miss(const SceneCommon& c, const PathState&
 // are visible from its entry point are known.  Ray::reflect / refract (rt.rs:559-589), the transmission lottery
 // (rt.rs:1051-1059) and the step of RayTracer::reduce_light (rt.rs:956-994, evaluated forward).  Adds the segment's
 // radiance to `acc` and advances `p` to the next ray; returns true when the path ended here (emission, bounce limit).
+// `hp` = the entry point p.o + p.d * h.t0 (the caller's: the pinhole loop carries it instead of p.o and h.t0; p.o is only
+// read for the exit point of a transmission).
 template <uint32_t F>
 __device__ __forceinline__ bool shade_hit(const SceneCommon& c, const FilmParams& fp, uint32_t pix, uint32_t sample, PathState& p, f3& acc,
-                                          const HitRec& h, uint32_t vis) {
+                                          const HitRec& h, uint32_t vis, f3 hp) {
     const f3 o = p.o, d = p.d;
     MRT_CHECK(h.inst >= 0 && (uint32_t)h.inst < c.n_inst);
     const FatInst* fat = c.fat + h.inst;
     Surf s;
     load_surf(fat, &s);
-    f3 hp = fma3(d, h.t0, o);
     f3 pl = to_local(s, hp);
     f3 n = surf_normal<F>(c, s, pl, h.tri0);
     Mat m;
@@ -147,6 +148,22 @@ __device__ __forceinline__ bool shade_hit(const SceneCommon& c, const FilmParams
     return false;
 }
 
+// Light visibility from a hit's entry point: shadow rays without a distance limit, rt.rs:1027-1045.
+template <class V, uint32_t F>
+__device__ __forceinline__ uint32_t light_visibility(const V& sc, f3 o, f3 d, const HitRec& h) {
+    uint32_t vis = 0;
+    if constexpr ((F & F_LIGHTS) != 0) {
+        const SceneCommon& c = sc.c();
+        const f3 hp = fma3(d, h.t0, o);
+        for (uint32_t li = 0; li < MRT_N_LIGHTS(c); li++) {
+            const f3 l = light_vec(c, li, hp);
+            HitRec dummy;
+            if (!closest_hit<V, F, true, false>(sc, fma3(l, MRT_E, hp), l, &dummy)) vis |= 1u << li;
+        }
+    }
+    return vis;
+}
+
 // One path segment: RaytraceIterator::next (rt.rs:1014-1066) — closest hit of the ray, light visibility from the entry
 // point (shadow rays without a distance limit, rt.rs:1027-1045) — then shade_hit.  Returns true when the path ended.
 template <class V, uint32_t F>
@@ -158,16 +175,8 @@ __device__ __forceinline__ bool path_segment(const V& sc, const FilmParams& fp, 
         return true;
     }
     if (MRT_HAS_SPHERE && MRT_REFINE_SPHERES(c)) refine_sphere_hit(c, p.o, p.d, &h);
-    uint32_t vis = 0;
-    if constexpr ((F & F_LIGHTS) != 0) {
-        const f3 hp = fma3(p.d, h.t0, p.o);
-        for (uint32_t li = 0; li < MRT_N_LIGHTS(c); li++) {
-            const f3 l = light_vec(c, li, hp);
-            HitRec dummy;
-            if (!closest_hit<V, F, true, false>(sc, fma3(l, MRT_E, hp), l, &dummy)) vis |= 1u << li;
-        }
-    }
-    return shade_hit<F>(c, fp, pix, sample, p, acc, h, vis);
+    const uint32_t vis = light_visibility<V, F>(sc, p.o, p.d, h);
+    return shade_hit<F>(c, fp, pix, sample, p, acc, h, vis, fma3(p.d, h.t0, p.o));
 }
 
 // Pixel of this thread.  Tiled: a warp renders an 8x4 tile and a block 16x8, so the lanes of a warp look at
@@ -186,11 +195,94 @@ __device__ __forceinline__ void thread_pixel(const FilmParams& fp, uint32_t* px,
 }
 
 // The megakernel body, one thread per supersampled pixel: the lane renders its pixel's samples back to back.
+// The megakernel body for a PINHOLE camera (aperture 0: the default of every example scene but dof.json and Mesh.json).
+// The lens jitter is (u - 0.5) * 0, so every sample of a pixel starts with the same ray and finds the same first hit (and
+// the same lights visible from it).  Ray, hit and visibility are computed once per pixel by the same arithmetic as
+// camera_ray / path_segment (bit-identical images, tests/test_gpu_parity.py), and the loop is rotated: an iteration is
+// shade -> search, a new path starts at the cached hit.  Against the thin-lens loop below this removes
+//   * the ~50-instruction path start (lens hash, normalisation, camera rotation) that ~4 lanes of a warp ran in 96 % of
+//     the iterations (ncu, profiles/r2_path_kernel_jit_ncu_summary.txt: 12.5 % of the issued instructions at 6.7 lanes), and
+//   * one closest-hit search per path: a path of k hits takes k iterations, whether it ends on a light, at the bounce
+//     limit or by leaving the scene (before: k + 1 when it left the scene; CornellBox2: 6.71 -> 6.18 iterations per path).
+template <class V, uint32_t F>
+__device__ __forceinline__ void path_body_pinhole(const V sc, const FilmParams& fp) {
+    // what a new path starts from, per thread, in shared memory (read by the few lanes that start a path in an iteration;
+    // in registers it would cost the kernel a resident block per SM): ray direction + t0 of the first hit, instance,
+    // visible lights, and for transmitting scenes / meshes the exit parameter and the triangles
+    __shared__ float4 s_dt[128];
+    __shared__ int s_inst[128];
+    __shared__ uint32_t s_vis[(F & F_LIGHTS) != 0 ? 128 : 1];
+    __shared__ float s_t1[(F & F_TRANSMIT) != 0 ? 128 : 1];
+    __shared__ int2 s_tri[(F & F_MESH) != 0 ? 128 : 1];
+    constexpr bool T1 = (F & F_TRANSMIT) != 0;
+    uint32_t px, py;
+    thread_pixel(fp, &px, &py);
+    if (px >= fp.nw || py >= fp.nh || fp.n_samples == 0u) return;
+    const SceneCommon& c = sc.c();
+    const uint32_t pix = py * fp.nw + px;
+    f3 acc = mk(0.f, 0.f, 0.f);
+    PathState p;
+    HitRec h;
+    camera_ray(fp, pixel_focus_vec(fp, px, py), 0.5f, 0.5f, &p.o, &p.d);
+    p.T = mk(1.f, 1.f, 1.f); p.pwr = 1.0f; p.bounce = 0;
+    if (!closest_hit<V, F, false, T1>(sc, p.o, p.d, &h)) {
+        // the pixel looks past the scene: every sample is sky.color (rt.rs:958), added one by one like the other loop does
+        for (uint32_t j = 0; j < fp.n_samples; j++) path_miss(c, p, acc);
+    } else {
+        if (MRT_HAS_SPHERE && MRT_REFINE_SPHERES(c)) refine_sphere_hit(c, p.o, p.d, &h);
+        uint32_t vis = light_visibility<V, F>(sc, p.o, p.d, h);
+        s_dt[threadIdx.x] = make_float4(p.d.x, p.d.y, p.d.z, h.t0);
+        s_inst[threadIdx.x] = h.inst;
+        if constexpr ((F & F_LIGHTS) != 0) s_vis[threadIdx.x] = vis;
+        if constexpr (T1) s_t1[threadIdx.x] = h.t1;
+        if constexpr ((F & F_MESH) != 0) s_tri[threadIdx.x] = make_int2(h.tri0, h.tri1);
+        f3 hp = mk(0.f, 0.f, 0.f);
+        p.bounce = MRT_NEED_PATH;
+        uint32_t j = 0;
+        // (a path starts at the TOP of the iteration after the one it ended in, behind a state flag, as in the thin-lens
+        // loop: written at the tail, where the path ends, the compiler nests the loops — an inner one per path — and the
+        // lanes of a warp wait for each other's paths to end)
+        for (;;) {
+            if (p.bounce == MRT_NEED_PATH) {
+                if (j >= fp.n_samples) break;
+                uint32_t tid;  // re-read here: kept in a register across the loop it would be the 49th (one resident block per SM less)
+                asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+                const float4 dt = s_dt[tid];
+                p.d = mk(dt.x, dt.y, dt.z);
+                p.o = fma3(p.d, MRT_E, mk(fp.cam_pos[0], fp.cam_pos[1], fp.cam_pos[2]));  // Ray::cast_default, rt.rs:555-557
+                hp = fma3(p.d, dt.w, p.o);
+                p.T = mk(1.f, 1.f, 1.f); p.pwr = 1.0f; p.bounce = 0;
+                h.t0 = dt.w; h.inst = s_inst[tid];
+                if constexpr ((F & F_LIGHTS) != 0) vis = s_vis[tid];
+                if constexpr (T1) h.t1 = s_t1[tid];
+                if constexpr ((F & F_MESH) != 0) { const int2 tr = s_tri[tid]; h.tri0 = tr.x; h.tri1 = tr.y; }
+            }
+            bool ended = shade_hit<F>(c, fp, pix, fp.sample0 + j * fp.sample_stride, p, acc, h, vis, hp);
+            if (!ended) {
+                if (!closest_hit<V, F, false, T1>(sc, p.o, p.d, &h)) {
+                    path_miss(c, p, acc);
+                    ended = true;
+                } else {
+                    if (MRT_HAS_SPHERE && MRT_REFINE_SPHERES(c)) refine_sphere_hit(c, p.o, p.d, &h);
+                    vis = light_visibility<V, F>(sc, p.o, p.d, h);
+                    hp = fma3(p.d, h.t0, p.o);
+                }
+            }
+            if (ended) { p.bounce = MRT_NEED_PATH; j++; }
+        }
+    }
+    MRT_CHECK(pix < fp.nw * fp.nh);
+    float4 a = fp.accum[pix];
+    a.x += acc.x; a.y += acc.y; a.z += acc.z;
+    fp.accum[pix] = a;
+}
+
 // LENS: how camera rays start — LENS_PINHOLE / LENS_THIN compile one case in (the specialised kernel has an entry point
 // for each), LENS_ANY decides at run time (the offline-built generic kernels).
 enum : int { LENS_PINHOLE = 0, LENS_THIN = 1, LENS_ANY = 2 };
 template <class V, uint32_t F, int LENS = LENS_ANY>
 __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
+    if constexpr (LENS == LENS_PINHOLE) { path_body_pinhole<V, F>(sc, fp); return; }
     uint32_t px, py;
     thread_pixel(fp, &px, &py);
     if (px >= fp.nw || py >= fp.nh || fp.n_samples == 0u) return;

@@ -306,6 +306,7 @@ int mrt_scene_upload(mrt_ctx* c, const mrt_scene* s) {
             d.v0 = make_float4(p[0], p[1], p[2], u2f((uint32_t)tri_leaf.size()));
             d.e0 = make_float4(p[3] - p[0], p[4] - p[1], p[5] - p[2], u2f((uint32_t)occ[t].size()));
             d.e1 = make_float4(p[6] - p[0], p[7] - p[1], p[8] - p[2], 0.0f);
+            d.pad = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             tris.push_back(d);
             tri_leaf.insert(tri_leaf.end(), occ[t].begin(), occ[t].end());
         }
@@ -484,7 +485,7 @@ int mrt_scene_upload(mrt_ctx* c, const mrt_scene* s) {
     // Scenes with a mesh always go through the scene BVH, whatever their size: its flat walk (mrt_device.cuh: bvh_walk) runs
     // the triangle BVH of a mesh instance in the same loop as the scene's nodes (MRT_MESH_VIA_BVH=0: A/B knob).
     const bool want_bvh = brute_cost > bvh_min || (c->knobs.mesh_via_bvh && !by_kind[K_MESH].empty());
-    bool use_bvh = want_bvh && !prim_boxes.empty() && prim_boxes_ok && prim_boxes.size() < (1u << 28) && !c->knobs.no_bvh;
+    bool use_bvh = want_bvh && !prim_boxes.empty() && prim_boxes_ok && prim_boxes.size() < (1u << 24) && !c->knobs.no_bvh;  // leaf references keep 24 bits of index (bvh_leaf)
     if (use_bvh) use_bvh = bvh_build_bounded(prim_boxes, &bvh_nodes, c->knobs.bvh_sah, &bvh_root);
     CK(c->d_bvh.upload(bvh_nodes, c->stream));
     CK(c->d_mesh_m.upload(mesh_m, c->stream));

@@ -94,6 +94,48 @@ def test_shared_rng_paths_match_oracle(pair, name, res, ssaa):
     assert abs(ag[fin].mean() - ac[fin].mean()) <= 0.03 * abs(ac[fin].mean()) + 1e-4
 
 
+@pytest.mark.parametrize("name,res,ssaa", CASES)
+def test_pinhole_entry_point_traces_the_thin_lens_paths(name, res, ssaa, monkeypatch):
+    """Aperture 0 (`--cam aprt: 0`): the specialised kernel's pinhole entry point (path_body_pinhole: camera ray, first hit
+    and its light visibility computed once per pixel, loop rotated to shade -> search) must trace the very paths of the
+    thin-lens loop with zero jitter: accumulators equal to those of the thin-lens entry point of the same cubin
+    (MRT_NO_PINHOLE) to the last bits, and the oracle's paths with shared random numbers like every other camera."""
+    from micro_raytracer_b200.sampler import JIT_FORCE, OPT_JIT
+    r = load(name, res, ssaa)
+    r.frame.cam.aprt = 0.0
+    acc = {}
+    for knob in ("thin", "pinhole"):
+        if knob == "thin":
+            monkeypatch.setenv("MRT_NO_PINHOLE", "1")  # read by mrt_create
+        else:
+            monkeypatch.delenv("MRT_NO_PINHOLE", raising=False)
+        g = mrt.Sampler(device=0)
+        g.set_option(OPT_JIT, JIT_FORCE)
+        # two calls of different size: the first hit is re-derived per launch, the sample indices carry on
+        g.execute(r.scene, r.frame, r.rt, 1)
+        g.sync()  # (a one-pass call is deferred and would be coalesced with the next: flush it)
+        g.execute(r.scene, r.frame, r.rt, 3)
+        acc[knob], n = g.accum()
+        assert n == 4
+        st = g.jit_status()
+        assert st["compiled"] and st["launches"] == 2, st
+        g.close()
+    assert np.isfinite(acc["pinhole"]).all()
+    # same paths, same arithmetic — but two functions to the compiler, which contracts a*b+c into FMAs in each on its own:
+    # bit-identical on most scenes (CornellBox2, CornellBox, Default, dof at the time of writing), last-bit differences on others
+    same = (acc["thin"] == acc["pinhole"]).all(axis=2).mean()
+    print(f"{name}: {same:.4%} of the pixels bit-identical between the two entry points")
+    ok = np.abs(acc["thin"] - acc["pinhole"]).max(axis=2) <= 1e-5 + 1e-5 * np.abs(acc["thin"]).max(axis=2)
+    assert ok.mean() >= 0.995, f"{name}: only {ok.mean():.4%} of the pixels agree to 1e-5"
+    cpu = oracle_lib.OracleSampler()
+    cpu.execute(r.scene, r.frame, r.rt, 4)
+    ac, _ = cpu.accum()
+    ok = np.abs(acc["pinhole"] - ac).max(axis=2) <= 2e-3 + 2e-3 * np.abs(ac).max(axis=2)
+    assert ok.mean() >= 0.95, f"{name}: only {ok.mean():.4%} pixels match the oracle"
+    fin = np.isfinite(ac).all(axis=2)
+    assert abs(acc["pinhole"][fin].mean() - ac[fin].mean()) <= 0.03 * abs(ac[fin].mean()) + 1e-4
+
+
 @pytest.mark.parametrize("name,res,ssaa", [("Default", (320, 180), 1.0), ("dof", (256, 144), 1.0), ("Minecraft", (160, 90), 1.0)])
 def test_direct_light_mode_is_deterministic_parity(pair, name, res, ssaa):
     """--bounce 0, aprt 0: one segment + direct light, no live randomness except the material

@@ -1,7 +1,7 @@
 """Throughput of every BASELINE.json config (not the headline bench): Mpaths/s per scene on one GPU,
 render-only (CUDA-event seconds returned by mrt_execute), at the configs' full resolutions with a
 bounded number of passes; optionally the oracle's rate on the host cores beside it.
-    python tools/bench_scenes.py [--cpu] [--only Scene] [--passes N]
+    python tools/bench_scenes.py [--cpu] [--only Scene] [--only3] [--passes N] [--pinhole]
 """
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -25,12 +25,16 @@ def main():
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     force_passes = int(sys.argv[sys.argv.index("--passes") + 1]) if "--passes" in sys.argv else None
     only3 = "--only3" in sys.argv  # the three scenes that are searched through a BVH
+    pinhole = "--pinhole" in sys.argv  # aperture 0 instead of the scene's (default 0.001): the specialised kernel's pinhole entry point
     rows = []
     for label, name, res, ssaa, rt, passes in CONFIGS:
         if (only and name != only) or (only3 and name not in ("Mesh", "Instance", "Minecraft")):
             continue
         passes = force_passes or passes
         r = load(name, res, ssaa, **rt)
+        if pinhole:
+            r.frame.cam.aprt = 0.0
+            label += " [aprt 0]"
         s = mrt.Sampler(device=0)
         s.execute(r.scene, r.frame, r.rt, 1)  # upload + warm-up; starts the background scene specialisation
         t_wait = time.time()
