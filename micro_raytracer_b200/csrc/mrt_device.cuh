@@ -86,8 +86,13 @@ static_assert(sizeof(FatInst) == 128, "FatInst must be one cache line");
 // ref.x / ref.y = child references: bit 31 set = leaf, the low bits are the primitive (scene BVH: kind << 28 |
 // index within the kind's table; mesh BVH: triangle index within the mesh), else the index of the child node.
 // One primitive per leaf, so leaves need no node at all.
-struct BvhNode { float4 q0, q1, q2; uint4 ref; };
-static_assert(sizeof(BvhNode) == 64, "a BVH node is read as two 32-byte words");
+// 48 bytes, three 16-byte words: the BVH kernels are bound by the L1 data pipe (ncu, Instance.json: l1tex__data_pipe_lsu_wavefronts
+// 81 % of peak at 64 % issue; the node reads of the divergent walks are 4/5 of the wavefronts, and a 256-bit load costs two), so
+// the six half extents are stored as fp16 ROUNDED UP — a node box may only grow: the candidate set stays a superset and the
+// results bit-identical — and a visit reads three words instead of four:
+//   w0 = (cL.x, cR.x, cL.y, cR.y)   w1 = (cL.z, cR.z, h2(hL.x, hR.x), h2(hL.y, hR.y))   w2 = (h2(hL.z, hR.z), 0, ref.x, ref.y)
+struct BvhNode { float4 w0; float2 cz; uint32_t hx, hy; uint32_t hz, pad, refl, refr; };
+static_assert(sizeof(BvhNode) == 48, "a BVH node is three 16-byte words");
 #define MRT_BVH_LEAF 0x80000000u
 struct DLight { float4 v_kind; float4 color_pwr; };  // v.xyz (pos or unit -dir), w = kind bits ; color.rgb, pwr
 struct DTex { uint32_t w, h, first, has_dat; };      // texel offset into the float4 texel array
@@ -267,6 +272,23 @@ __device__ __forceinline__ void node_slabs(const NodeRay& n, float4 q0, float4 q
     up2(fma2(hz, bc2(n.bam.z), cz), hza, hzb);
     *tnl = fmaxf(fmaxf(lxa, lya), lza); *tfl = fminf(fminf(hxa, hya), hza);
     *tnr = fmaxf(fmaxf(lxb, lyb), lzb); *tfr = fminf(fminf(hxb, hyb), hzb);
+}
+
+// fp16 pair -> two floats (cvt.f32.f16 x 2; no cuda_fp16.h under NVRTC)
+__device__ __forceinline__ void half2_to_floats(uint32_t u, float& lo, float& hi) {
+    asm("{\n\t.reg .b16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}" : "=f"(lo), "=f"(hi) : "r"(u));
+}
+// One node visit's data: three 16-byte loads, the half extents widened to f32, in node_slabs' operand layout.
+__device__ __forceinline__ void load_node(const BvhNode* p, float4* q0, float4* q1, float4* q2, uint2* ref) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    const uint4 w2 = __ldg(reinterpret_cast<const uint4*>(p) + 2);
+    *q0 = w0;
+    q1->x = w1.x; q1->y = w1.y;
+    half2_to_floats(__float_as_uint(w1.z), q1->z, q1->w);
+    half2_to_floats(__float_as_uint(w1.w), q2->x, q2->y);
+    half2_to_floats(w2.x, q2->z, q2->w);
+    *ref = make_uint2(w2.z, w2.w);
 }
 
 // ------------------------------------------------------------------ RNG: pcg4d counter hash
@@ -468,9 +490,9 @@ __device__ __forceinline__ bool mesh_test_bvh(const SceneCommon& c, const DMesh&
             }
         } else {
             MRT_CHECK(cur < c.n_tbvh);
-            const f8 n01 = ldg256(&c.tbvh[cur].q0), n23 = ldg256(&c.tbvh[cur].q2);
-            const float4 q0 = n01.lo, q1 = n01.hi, q2 = n23.lo;
-            const uint2 ref = make_uint2(__float_as_uint(n23.hi.x), __float_as_uint(n23.hi.y));
+            float4 q0, q1, q2;
+            uint2 ref;
+            load_node(&c.tbvh[cur], &q0, &q1, &q2, &ref);
             float tl, tfl, tr, tfr;
             node_slabs(nr, q0, q1, q2, &tl, &tfl, &tr, &tfr);
             bool hl = !(tl > tfl || tfl < 0.0f), hr = !(tr > tfr || tfr < 0.0f);
@@ -876,9 +898,9 @@ __device__ __forceinline__ void bvh_traverse(Best& B, const GlobalScene& s, cons
             if constexpr (ANY) { if (B.any) return; }
         } else {
             MRT_CHECK(cur < c_n_bvh);
-            const f8 n01 = ldg256(&s.bvh[cur].q0), n23 = ldg256(&s.bvh[cur].q2);
-            const float4 q0 = n01.lo, q1 = n01.hi, q2 = n23.lo;
-            const uint2 ref = make_uint2(__float_as_uint(n23.hi.x), __float_as_uint(n23.hi.y));
+            float4 q0, q1, q2;
+            uint2 ref;
+            load_node(&s.bvh[cur], &q0, &q1, &q2, &ref);
             float tl, tfl, tr, tfr;
             node_slabs(r.n, q0, q1, q2, &tl, &tfl, &tr, &tfr);
             // '<=': an equal t0 with a lower index must still be found

@@ -198,7 +198,7 @@ __device__ __forceinline__ void thread_pixel(const FilmParams& fp, uint32_t* px,
 // The megakernel body for a PINHOLE camera (aperture 0: the default of every example scene but dof.json and Mesh.json).
 // The lens jitter is (u - 0.5) * 0, so every sample of a pixel starts with the same ray and finds the same first hit (and
 // the same lights visible from it).  Ray, hit and visibility are computed once per pixel by the same arithmetic as
-// camera_ray / path_segment (bit-identical images, tests/test_gpu_parity.py), and the loop is rotated: an iteration is
+// camera_ray / path_segment (the same paths; images equal to the last bits, tests/test_gpu_parity.py), and the loop is rotated: an iteration is
 // shade -> search, a new path starts at the cached hit.  Against the thin-lens loop below this removes
 //   * the ~50-instruction path start (lens hash, normalisation, camera rotation) that ~4 lanes of a warp ran in 96 % of
 //     the iterations (ncu, profiles/r2_path_kernel_jit_ncu_summary.txt: 12.5 % of the issued instructions at 6.7 lanes), and

@@ -61,6 +61,29 @@ bool all_finite(const float* v, int n) {
     return true;
 }
 
+// A non-negative float as fp16 bits, rounded UP (towards +inf): the half extents of a BVH node may only grow.  Values above
+// the fp16 range become +inf (a box that is never culled), NaN is not expected (extents of finite boxes).
+uint32_t half_up(float v) {
+    if (!(v > 0.0f)) return 0u;
+    if (v > 65504.0f) return 0x7c00u;
+    uint32_t b;
+    std::memcpy(&b, &v, 4);
+    const int e = (int)(b >> 23) - 127;
+    uint32_t h;
+    if (e < -24) return 1u;  // below the smallest subnormal: round up to it
+    if (e < -14) {           // subnormal half: value = m * 2^-24
+        const float scaled = std::ldexp(v, 24);
+        h = (uint32_t)std::ceil(scaled);  // <= 1024: 1024 is the smallest normal, the bit pattern carries over
+    } else {
+        const uint32_t mant = b & 0x7fffffu;
+        h = ((uint32_t)(e + 15) << 10) | (mant >> 13);
+        if (mant & 0x1fffu) h += 1u;  // any dropped bit: next representable (the carry into the exponent is correct)
+    }
+    return h > 0x7c00u ? 0x7c00u : h;
+}
+uint32_t half2_up(float lo, float hi) { return half_up(lo) | (half_up(hi) << 16); }
+
+
 // ---- BVH builder (scene-level BVH over the finite instances, triangle BVHs of the meshes; mrt_device.cuh:
 // BvhNode): median split of the centroids along the widest axis, one primitive per leaf (measured best).
 struct PrimBox { float lo[3], hi[3]; uint32_t ref; };
@@ -163,10 +186,14 @@ uint32_t bvh_build(std::vector<PrimBox>& prims, size_t begin, size_t end, std::v
     centre_half(llo, lhi, cl, hl);
     centre_half(rlo, rhi, cr, hr);
     BvhNode& n = (*nodes)[node];
-    n.q0 = make_float4(cl[0], cr[0], cl[1], cr[1]);
-    n.q1 = make_float4(cl[2], cr[2], hl[0], hr[0]);
-    n.q2 = make_float4(hl[1], hr[1], hl[2], hr[2]);
-    n.ref = make_uint4(l, r, 0u, 0u);
+    n.w0 = make_float4(cl[0], cr[0], cl[1], cr[1]);
+    n.cz = make_float2(cl[2], cr[2]);
+    n.hx = half2_up(hl[0], hr[0]);
+    n.hy = half2_up(hl[1], hr[1]);
+    n.hz = half2_up(hl[2], hr[2]);
+    n.pad = 0u;
+    n.refl = l;
+    n.refr = r;
     return (uint32_t)node;
 }
 // The traversal stacks hold MRT_BVH_STACK entries.  SAH splits refuse lopsided cuts, so they stay far below that for any
