@@ -45,12 +45,7 @@ SCENES = os.path.join(ROOT, "tests", "golden", "scenes")
 SCENE = os.path.join(SCENES, "CornellBox2.json")
 # flops/path = 60 + S*sum_inst(36 + C_kind) + H*153, CornellBox2: sum_inst = 533,
 # S = 6.709 closest-hit calls and H = 6.178 hits per path (measured by the oracle, tests/test_oracle_stats.py)
-FLOPS_PER_PATH_REFERENCE = 60.0 + 6.709 * 533.0 + 6.178 * 153.0  # 4581: every path generates its camera ray and searches its first hit
-# CornellBox2 has a pinhole camera (aperture 0): camera ray and first hit are the same for every sample of a pixel, and the
-# kernel computes them once per pixel and launch (path_body_pinhole).  The roofline is charged with the work that is LEFT —
-# S - 1 searches per path — so that caching the first hit cannot push `frac` up; the reference-formulation figure is
-# reported beside it.
-FLOPS_PER_PATH = (6.709 - 1.0) * 533.0 + 6.178 * 153.0  # 3988
+FLOPS_PER_PATH = 60.0 + 6.709 * 533.0 + 6.178 * 153.0
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.45: SMs x lanes x FMA x max SM clock
 DATA = "the reference's own scene file (example/CornellBox2.json, kept under tests/golden/scenes); fully specified, no dataset"
 # BASELINE.json configs other than the headline: (label, scene, res, ssaa, rt overrides, passes rendered here)
@@ -342,15 +337,11 @@ def main():
                     "calls_per_step": {"mrt_set_scene": 1, "mrt_execute(ctx, 1)": my_passes, "mrt_img": 1},
                     "sequence": "the reference's loop, cli.rs:157-174: Sampler::new once; per step set_scene, one execute per pass, img"},
             "gpu_launches": int(lt.item()),
-            "roofline": {"bound": "fp32", "kernel": "path_kernel_jit_pinhole" if s.jit_status()["launches"] else "path_kernel_param<0>", "achieved": ach_tf, "peak": peak_tf,
+            "roofline": {"bound": "fp32", "kernel": "path_kernel_jit" if s.jit_status()["launches"] else "path_kernel_param<0>", "achieved": ach_tf, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
                          "peak_source": "FFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
                          "peak_nominal": FP32_NOMINAL_TFLOPS, "frac_of_nominal": ach_tf / FP32_NOMINAL_TFLOPS,
                          "flops_per_path": FLOPS_PER_PATH, "paths_per_launch": paths_per_launch, "launch_ms": launch_ms,
-                         "flops_per_path_note": "SURVEY 8(d) count minus the camera ray and the first closest-hit search of every path, which a pinhole camera "
-                                                "makes per-pixel constants (computed once per pixel and launch): (S-1)*533 + H*153",
-                         "flops_per_path_reference_formulation": FLOPS_PER_PATH_REFERENCE,
-                         "frac_reference_formulation": paths_per_launch * FLOPS_PER_PATH_REFERENCE / (launch_ms * 1e-3) / 1e12 / peak_tf,
                          "roofline_mpaths_per_gpu": FP32_NOMINAL_TFLOPS * 1e12 / FLOPS_PER_PATH / 1e6},
             "image_mean_u8": float(out_img.mean()),
             "jit": s.jit_status(),

@@ -195,7 +195,7 @@ __device__ __forceinline__ void thread_pixel(const FilmParams& fp, uint32_t* px,
 }
 
 // The megakernel body, one thread per supersampled pixel: the lane renders its pixel's samples back to back.
-// The megakernel body for a PINHOLE camera (aperture 0: the default of every example scene but dof.json and Mesh.json).
+// The megakernel body for a PINHOLE camera (aperture 0; the reference's default is 0.001, so only frames that ask for it).
 // The lens jitter is (u - 0.5) * 0, so every sample of a pixel starts with the same ray and finds the same first hit (and
 // the same lights visible from it).  Ray, hit and visibility are computed once per pixel by the same arithmetic as
 // camera_ray / path_segment (the same paths; images equal to the last bits, tests/test_gpu_parity.py), and the loop is rotated: an iteration is
@@ -289,10 +289,11 @@ __device__ __forceinline__ void path_body(const V sc, const FilmParams& fp) {
     const uint32_t pix = py * fp.nw + px;
     f3 q = pixel_focus_vec(fp, px, py);
     const uint32_t cam_seed = cam_hash_seed(pix, fp.key);
-    // Pinhole camera (aperture 0, the default of every example scene but dof.json): the lens jitter is (u - 0.5) * 0, so
-    // every sample of a pixel starts with the same ray.  Its direction is computed once, here, by the very same
-    // arithmetic (camera_ray with zero jitter: bit-identical images), and starting a path shrinks from ~50 instructions
-    // — lens hash, normalisation, camera rotation; run by ~4 lanes of the warp in 96 % of the loop's iterations — to 11.
+    // Pinhole camera (aperture 0 — not the reference's default, which is 0.001, parser.rs:206): the lens jitter is
+    // (u - 0.5) * 0, so every sample of a pixel starts with the same ray.  The generic kernels compute its direction once,
+    // here, by the very same arithmetic (camera_ray with zero jitter), and starting a path shrinks from ~50 instructions
+    // — lens hash, normalisation, camera rotation; run by ~5 lanes of the warp in 96 % of the loop's iterations — to 11.
+    // (The specialised kernel goes further for such frames: path_body_pinhole.)
     const bool pinhole = LENS == LENS_PINHOLE || (LENS == LENS_ANY && fp.aprt == 0.0f);  // warp-uniform
     if (pinhole) { f3 o0; camera_ray(fp, q, 0.5f, 0.5f, &o0, &q); }  // q := the pixel's ray direction
 

@@ -623,3 +623,92 @@ __device__ __forceinline__ void path_body_wave(const V sc, const FilmParams& fp)
 }
 
 #endif
+
+
+// ======================================================================================================================
+// 4. (round 2, second session) Thin-lens loop with pre-generated camera rays — measured on the headline scene, B200:
+//    plain loop 13 941 Mpaths/s; cadence 2: 13 178, cadence 4: 13 683, cadence 8: 13 425.  Rejected: the pop, the cadence
+//    test and the spill-free bookkeeping cost what the rarer path starts save (the loop's dynamic instruction count is
+//    unchanged, ~340 per iteration), and the latency of the path-start chain was already hidden by the other warps.
+//    A first version with an idle state (a lane without a spare ray waits for the next top-up) ran at HALF speed: the compiler
+//    left out the reconvergence point behind the path-start block (a `break` inside it), so the lanes that had just popped
+//    a ray ran the whole segment code apart from the others.  Code as it ran (path_body dispatched LENS_THIN to it):
+// ======================================================================================================================
+#if 0
+// Thin-lens loop with PRE-GENERATED camera rays (MRT_RING = cadence in iterations, a power of two; experiment).
+// In the plain loop below the ~50-instruction path start runs in 96 % of the iterations for the ~5 lanes that need it: 12.5 % of
+// the issued instructions and 19 % of the stall samples of the headline kernel (long dependent chain: hash -> int-to-float ->
+// normalise -> MUFU.RSQ).  Here every lane keeps up to two ready rays in shared memory; all lanes top their rings up TOGETHER,
+// one ray per lane, every MRT_RING-th iteration (the iteration counter is the same in every lane of a warp: no vote), and
+// starting a path is a pop: two shared-memory loads.  A lane that has used up both spares before the next top-up (a run
+// of very short paths) makes its ray on the spot, as the plain loop does.  Rays are keyed by the sample index, every lane
+// still renders its samples in order: the image does not change by a bit.
+#ifdef MRT_RING
+template <class V, uint32_t F>
+__device__ __forceinline__ void path_body_ring(const V sc, const FilmParams& fp) {
+    __shared__ float4 s_q[128];        // q.xyz (pixel_focus_vec), lens seed (bits)
+    __shared__ float4 s_od[2][128];    // ring slot: o.xyz, d.x
+    __shared__ float2 s_dd[2][128];    //            d.y, d.z
+    uint32_t px, py;
+    thread_pixel(fp, &px, &py);
+    if (px >= fp.nw || py >= fp.nh || fp.n_samples == 0u) return;
+    const uint32_t pix = py * fp.nw + px;
+    {
+        const f3 q = pixel_focus_vec(fp, px, py);
+        s_q[threadIdx.x] = make_float4(q.x, q.y, q.z, __uint_as_float(cam_hash_seed(pix, fp.key)));
+    }
+    f3 acc = mk(0.f, 0.f, 0.f);
+    PathState p;
+    p.o = mk(0.f, 0.f, 0.f); p.d = mk(0.f, 1.f, 0.f); p.T = mk(1.f, 1.f, 1.f);
+    p.pwr = 1.0f;
+    p.bounce = MRT_NEED_PATH;
+    uint32_t g = 0;  // rays generated so far: sample g goes to slot g & 1
+    uint32_t c = 0;  // paths started so far; the running path is sample c - 1
+    for (uint32_t it = 0;; it++) {
+        if ((it & (uint32_t)(MRT_RING - 1)) == 0u) {
+            if (g - c < 2u && g < fp.n_samples) {
+                uint32_t tid;
+                asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+                const float4 qs = s_q[tid];
+                const float2 u = rng_cam(__float_as_uint(qs.w), fp.sample0 + g * fp.sample_stride);
+                f3 o, d;
+                camera_ray(fp, mk(qs.x, qs.y, qs.z), u.x, u.y, &o, &d);
+                s_od[g & 1u][tid] = make_float4(o.x, o.y, o.z, d.x);
+                s_dd[g & 1u][tid] = make_float2(d.y, d.z);
+                g++;
+            }
+        }
+        // (no `break` inside this block: with one the compiler leaves out the reconvergence point behind it, and the lanes
+        // that have just started a path run the whole segment code apart from the others)
+        if (p.bounce == MRT_NEED_PATH && c < fp.n_samples) {
+            uint32_t tid;
+            asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+            if (c < g) {
+                const float4 od = s_od[c & 1u][tid];
+                const float2 dd = s_dd[c & 1u][tid];
+                p.o = mk(od.x, od.y, od.z); p.d = mk(od.w, dd.x, dd.y);
+            } else {  // both spares used up since the last top-up (a run of very short paths): make the ray here
+                const float4 qs = s_q[tid];
+                const float2 u = rng_cam(__float_as_uint(qs.w), fp.sample0 + c * fp.sample_stride);
+                camera_ray(fp, mk(qs.x, qs.y, qs.z), u.x, u.y, &p.o, &p.d);
+                g = c + 1u;
+            }
+            p.T = mk(1.f, 1.f, 1.f);
+            p.pwr = 1.0f;
+            p.bounce = 0;
+            c++;
+        }
+        if (p.bounce == MRT_NEED_PATH) break;  // all samples rendered
+        // (every lane that is still in the loop runs a segment: no lane ever waits for a ray, and the loop keeps the shape
+        // of the plain one — with an idle state the compiler let the lanes that had just popped a ray run the whole segment
+        // code a second time, apart from the others: half the speed)
+        if (path_segment<V, F>(sc, fp, pix, fp.sample0 + (c - 1u) * fp.sample_stride, p, acc)) p.bounce = MRT_NEED_PATH;
+    }
+    MRT_CHECK(pix < fp.nw * fp.nh);
+    float4 a = fp.accum[pix];
+    a.x += acc.x; a.y += acc.y; a.z += acc.z;
+    fp.accum[pix] = a;
+}
+#endif
+
+#endif
