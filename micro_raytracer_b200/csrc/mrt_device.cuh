@@ -648,7 +648,19 @@ __device__ __forceinline__ void best_update_slab(Best& B, float t0, float t1, in
                 "selp.f32 %0, %2, %0, q;\n\t"
                 "selp.b32 %1, %4, %1, q;\n\t}"
                 : "+f"(B.t0), "+r"(B.bi) : "f"(t0), "f"(t1), "r"(idx));
-        else
+        else {
+#ifndef MRT_T1_SIGN_ON_ALU_PIPE  // t1 >= 0 folded into the minimum through u = t1 * inf (+inf / -inf / NaN for t1 > / < / = 0;
+            // min ignores a NaN): one FMUL on the FMA pipe + FMNMX3 instead of FMNMX + FSETP on the half-rate ALU pipe
+            // (same predicate; headline +0.4 %: 13 969 -> 14 021 Mpaths/s, two runs each)
+            asm("{\n\t.reg .pred q;\n\t.reg .f32 tm, u;\n\t"
+                "mul.ftz.f32 u, %3, 0f7F800000;\n\t"
+                "min.ftz.f32 tm, %3, %0;\n\t"
+                "min.ftz.f32 tm, tm, u;\n\t"
+                "setp.lt.ftz.f32 q, %2, tm;\n\t"
+                "selp.f32 %0, %2, %0, q;\n\t"
+                "selp.b32 %1, %4, %1, q;\n\t}"
+                : "+f"(B.t0), "+r"(B.bi) : "f"(t0), "f"(t1), "r"(idx));
+#else
             asm("{\n\t.reg .pred p, q;\n\t.reg .f32 tm;\n\t"
                 "min.ftz.f32 tm, %3, %0;\n\t"
                 "setp.ge.ftz.f32 p, %3, 0f00000000;\n\t"
@@ -656,6 +668,8 @@ __device__ __forceinline__ void best_update_slab(Best& B, float t0, float t1, in
                 "selp.f32 %0, %2, %0, q;\n\t"
                 "selp.b32 %1, %4, %1, q;\n\t}"
                 : "+f"(B.t0), "+r"(B.bi) : "f"(t0), "f"(t1), "r"(idx));
+#endif
+        }
     }
 }
 

@@ -11,7 +11,11 @@ def last_json(path):
 
 def copy_json(src, dst):
     if os.path.exists(os.path.join(G, src)):
-        json.dump(last_json(os.path.join(G, src)), open(os.path.join(P, dst), "w"), indent=1)
+        try:
+            obj = json.load(open(os.path.join(G, src)))  # a whole-file JSON document
+        except Exception:  # noqa: BLE001
+            obj = last_json(os.path.join(G, src))        # log lines, then one JSON line
+        json.dump(obj, open(os.path.join(P, dst), "w"), indent=1)
 
 
 def ncu_summary(rep, dst, paths=None):
@@ -52,12 +56,13 @@ def main():
             copy_json(src, dst)
         except Exception as e:  # noqa: BLE001
             print("skip", src, e)
-    for f in ("r2_ncu_launch_list.csv", "r2_scenes.jsonl", "r2_checked_build_suite.txt", "r2_pytest_gpu.txt", "r2_smoke.txt"):
+    for f in ("r2_ncu_launch_list.csv", "r2_scenes.jsonl", "r2_scenes_pinhole.jsonl", "r2_checked_build_suite.txt", "r2_pytest_gpu.txt", "r2_smoke.txt"):
         if os.path.exists(os.path.join(G, f)):
             shutil.copy(os.path.join(G, f), os.path.join(P, f))
     head = ncu_summary("r2_path_kernel_jit.ncu-rep", "r2_path_kernel_jit_ncu_summary.txt", 4777574400)
     for name in ("Mesh", "Instance", "Minecraft"):
         ncu_summary(f"r2_{name}.ncu-rep", f"r2_{name.lower()}_ncu_summary.txt")
+    ncu_summary("r2_CornellBox2_pinhole.ncu-rep", "r2_cornellbox2_pinhole_ncu_summary.txt", 2160 * 2160 * 128)
     if head:
         def num(k):
             return float(head[k].replace(",", ""))

@@ -16,7 +16,13 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum",
         "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum", "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum",
         "sm__sass_thread_inst_executed_op_fp32_pred_on.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
-        "smsp__sass_average_branch_targets_threads_uniform.pct", "sm__inst_executed_pipe_fp16.avg.pct_of_peak_sustained_active"]
+        "smsp__sass_average_branch_targets_threads_uniform.pct", "sm__inst_executed_pipe_fp16.avg.pct_of_peak_sustained_active",
+        # the L1 data pipe: what bounds the BVH kernels (divergent node reads), DESIGN.md 4.1
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__t_sector_hit_rate.pct", "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__warps_eligible.avg.per_cycle_active"]
 print(f"# ncu summary of {rep}")
 for w in want:
     if w in hdr:
