@@ -104,13 +104,14 @@ def test_pinhole_entry_point_traces_the_thin_lens_paths(name, res, ssaa, monkeyp
     r = load(name, res, ssaa)
     r.frame.cam.aprt = 0.0
     acc = {}
-    for knob in ("thin", "pinhole"):
+    from micro_raytracer_b200.sampler import JIT_OFF
+    for knob in ("thin", "pinhole", "generic"):  # generic: the offline-built kernels, whose loop starts aperture-0 paths from the ray kept per pixel
         if knob == "thin":
             monkeypatch.setenv("MRT_NO_PINHOLE", "1")  # read by mrt_create
         else:
             monkeypatch.delenv("MRT_NO_PINHOLE", raising=False)
         g = mrt.Sampler(device=0)
-        g.set_option(OPT_JIT, JIT_FORCE)
+        g.set_option(OPT_JIT, JIT_OFF if knob == "generic" else JIT_FORCE)
         # two calls of different size: the first hit is re-derived per launch, the sample indices carry on
         g.execute(r.scene, r.frame, r.rt, 1)
         g.sync()  # (a one-pass call is deferred and would be coalesced with the next: flush it)
@@ -118,9 +119,14 @@ def test_pinhole_entry_point_traces_the_thin_lens_paths(name, res, ssaa, monkeyp
         acc[knob], n = g.accum()
         assert n == 4
         st = g.jit_status()
-        assert st["compiled"] and st["launches"] == 2, st
+        if knob == "generic":
+            assert st["launches"] == 0 and g.launch_count() >= 2, st
+        else:
+            assert st["compiled"] and st["launches"] == 2, st
         g.close()
     assert np.isfinite(acc["pinhole"]).all()
+    okg = np.abs(acc["generic"] - acc["pinhole"]).max(axis=2) <= 1e-3 + 2e-3 * np.abs(acc["pinhole"]).max(axis=2)
+    assert okg.mean() >= 0.97, f"{name}: generic kernel vs pinhole entry point: only {okg.mean():.4%} of the pixels agree"
     # same paths, same arithmetic — but two functions to the compiler, which contracts a*b+c into FMAs in each on its own:
     # bit-identical on most scenes (CornellBox2, CornellBox, Default, dof at the time of writing), last-bit differences on others
     same = (acc["thin"] == acc["pinhole"]).all(axis=2).mean()
