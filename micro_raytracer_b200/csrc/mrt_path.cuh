@@ -194,12 +194,11 @@ __device__ __forceinline__ void thread_pixel(const FilmParams& fp, uint32_t* px,
     }
 }
 
-// The megakernel body, one thread per supersampled pixel: the lane renders its pixel's samples back to back.
 // The megakernel body for a PINHOLE camera (aperture 0; the reference's default is 0.001, so only frames that ask for it).
 // The lens jitter is (u - 0.5) * 0, so every sample of a pixel starts with the same ray and finds the same first hit (and
 // the same lights visible from it).  Ray, hit and visibility are computed once per pixel by the same arithmetic as
-// camera_ray / path_segment (the same paths; images equal to the last bits, tests/test_gpu_parity.py), and the loop is rotated: an iteration is
-// shade -> search, a new path starts at the cached hit.  Against the thin-lens loop below this removes
+// camera_ray / path_segment (the same paths; images equal to the last bits, tests/test_gpu_parity.py), and the loop is
+// rotated: an iteration is shade -> search, a new path starts at the cached hit.  Against the thin-lens loop below this removes
 //   * the ~50-instruction path start (lens hash, normalisation, camera rotation) that ~4 lanes of a warp ran in 96 % of
 //     the iterations (ncu, profiles/r2_path_kernel_jit_ncu_summary.txt: 12.5 % of the issued instructions at 6.7 lanes), and
 //   * one closest-hit search per path: a path of k hits takes k iterations, whether it ends on a light, at the bounce
@@ -277,6 +276,7 @@ __device__ __forceinline__ void path_body_pinhole(const V sc, const FilmParams& 
     fp.accum[pix] = a;
 }
 
+// The megakernel body, one thread per supersampled pixel: the lane renders its pixel's samples back to back.
 // LENS: how camera rays start — LENS_PINHOLE / LENS_THIN compile one case in (the specialised kernel has an entry point
 // for each), LENS_ANY decides at run time (the offline-built generic kernels).
 enum : int { LENS_PINHOLE = 0, LENS_THIN = 1, LENS_ANY = 2 };
