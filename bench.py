@@ -266,9 +266,13 @@ def main():
     # one-time cost, like the warm-up steps themselves: with a cold kernel cache NVRTC needs ~0.5 s for the scene's specialised
     # kernel, and at N = 8 three warm-up steps last 0.14 s — without this wait the first timed steps would still run on the
     # generic kernel.  Bounded; a library without NVRTC stays on the generic kernel and says so in `jit` / `roofline.kernel`.
+    t_wait = time.time()
+
     def jit_pending():  # on ANY rank: render_step holds a collective, so every rank must take the same number of extra steps
         st = s.jit_status()
-        pending = st["eligible"] and not st["compiled"]
+        # (a compile that failed — no NVRTC on the box — reports its error and never becomes `compiled`: not pending)
+        pending = (st["eligible"] and not st["compiled"] and not st["error"] and time.time() - t_wait < 10.0
+                   and os.environ.get("MRT_JIT", "1") != "0")   # MRT_JIT=0: the generic-kernel A/B run, nothing to wait for
         if world > 1:
             flag = torch.tensor([1 if pending else 0], device=dev, dtype=torch.int32)
             dist.all_reduce(flag, op=dist.ReduceOp.MAX)
