@@ -441,6 +441,12 @@ def other_configs(device, with_cpu=True):
         st = s.jit_status()
         row = {"workload": label, "film": [nw, nh], "passes": passes, "mpaths_s": nw * nh * passes / sec / 1e6,
                "launch_ms": 1e3 * sec / -(-passes // s.spp_per_launch()), "jit": st["launches"] > 0, "kernel": s.kernel_info()}
+        # the same frame with aperture 0 (the scene's own is the reference's default 0.001, or what the file sets): the
+        # specialised kernel's pinhole entry point — first hit cached per pixel (same cubin: no further compile)
+        r.frame.cam.aprt = 0.0
+        s.reset()
+        sec0 = min(s.execute(r.scene, r.frame, r.rt, passes) for _ in range(2))
+        row["aperture0_mpaths_s"] = nw * nh * passes / sec0 / 1e6
         s.close()
         if with_cpu:
             import oracle_lib
